@@ -1,0 +1,113 @@
+// TEST-ONLY: compiles the product's per-env rules header
+// (twixt_for_open_spiel_b200/csrc/twixt_engine.cuh) for the HOST so that
+// `pytest -m "not gpu"` can check the rules, the crossing masks, the legal
+// selection and the Philox stream against the oracle without a GPU.  This
+// file is never part of libtwixt_b200.so: the product has no CPU path.
+// TW_TEST_STACK (default 48, tests also build with 2) sizes the flood stack
+// so the overflow branch is exercised.
+#include <cstdint>
+#include <cstring>
+
+#include "twixt_engine.cuh"
+#include "twixt_philox.cuh"
+
+#ifndef TW_TEST_STACK
+#define TW_TEST_STACK 48
+#endif
+
+using namespace twixt;
+using Rec = RecordRef<1>;
+
+extern "C" {
+
+int he_record_words(int n) { return record_words(n); }
+
+void he_init(uint32_t* rec, int n) {
+  Rec b{rec, n};
+  init_record(b);
+}
+
+int he_legal_actions(uint32_t* rec, int n, int64_t* out) {
+  Rec b{rec, n};
+  Header h;
+  load_header(b, h);
+  if (h.result != kOpen) return 0;
+  int c = 0;
+  for (int x = 0; x < n; ++x) {
+    uint32_t w = legal_word(b, h, x);
+    while (w) {
+      int y = tw_ctz(w);
+      w &= w - 1u;
+      out[c++] = x * n + y;
+    }
+  }
+  return c;
+}
+
+int he_legal_count(uint32_t* rec, int n) {
+  Rec b{rec, n};
+  Header h;
+  load_header(b, h);
+  return legal_count(h, n);
+}
+
+// 0 applied, 1 illegal (record untouched)
+int he_apply(uint32_t* rec, int n, int action) {
+  Rec b{rec, n};
+  Header h;
+  load_header(b, h);
+  if (!is_legal(b, h, action)) return 1;
+  apply_legal_cell<TW_TEST_STACK>(b, h, action / n, action % n);
+  store_header(b, h);
+  return 0;
+}
+
+int he_current_player(uint32_t* rec, int n) {
+  Rec b{rec, n};
+  Header h;
+  load_header(b, h);
+  return current_player(h);
+}
+
+void he_observation(uint32_t* rec, int n, float* out) {
+  Rec b{rec, n};
+  int w = n - 2;
+  for (int p = 0; p < 12; ++p)
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < w; ++c) {
+        int x, y;
+        obs_cell(n, p, r, c, x, y);
+        out[(p * n + r) * w + c] = ((obs_plane_word(b, p, x) >> y) & 1u) ? 1.0f : 0.0f;
+      }
+}
+
+int he_playout(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int max_plies, int64_t* actions_out) {
+  Rec b{rec, n};
+  Header h;
+  load_header(b, h);
+  int step = 0;
+  uint32_t r[4] = {0, 0, 0, 0};
+  while (h.result == kOpen && step < max_plies) {
+    if ((step & 3) == 0)
+      philox4x32_10(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
+                    static_cast<uint32_t>(step) >> 2, 0u, static_cast<uint32_t>(seed),
+                    static_cast<uint32_t>(seed >> 32), r);
+    int L = legal_count(h, n);
+    int k = static_cast<int>(playout_index(r[step & 3], static_cast<uint32_t>(L)));
+    int x, y;
+    select_legal(b, h, k, x, y);
+    if (actions_out) actions_out[step] = x * n + y;
+    apply_legal_cell<TW_TEST_STACK>(b, h, x, y);
+    ++step;
+  }
+  store_header(b, h);
+  return step;
+}
+
+void he_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+int he_select_bit(uint32_t w, int k) { return select_bit(w, k); }
+
+}  // extern "C"

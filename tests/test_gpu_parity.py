@@ -1,0 +1,317 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
+
+Every test plays oracle-generated games -- including swaps, draws and illegal
+moves -- through libtwixt_b200 in lock-step with the oracle and compares, at
+every ply: the ascending legal-action list, the legal mask, current player,
+terminal flag, returns, the observation tensor and the complete packed state
+record (pegs, links, blocked flags, border flags, counters).
+"""
+import random
+
+import numpy as np
+import pytest
+
+from helpers import SEED, draw_seeking_actions, pad_games, random_game_actions
+
+pytestmark = pytest.mark.gpu
+
+
+def _lockstep(oracle_mod, n, games, check_obs_every=1):
+    """Replay `games` (lists of actions) on the GPU batch and the oracle in lock-step."""
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    og = oracle_mod.OracleGame(n)
+    E = len(games)
+    batch = TwixTBatch(n, E, 0, SEED)
+    states = [og.new_initial_state() for _ in range(E)]
+    acts = pad_games(games)
+    maxlen = acts.shape[1]
+    for ply in range(maxlen + 1):
+        la, cnt = batch.legal_actions()
+        mask = batch.legal_mask()
+        player = batch.current_player()
+        term = batch.is_terminal()
+        rets = batch.returns()
+        recs = batch.export_state()
+        obs = batch.observation() if ply % check_obs_every == 0 or ply == maxlen else None
+        for e, st in enumerate(states):
+            ol = st.legal_actions()
+            assert la[e, :cnt[e]].tolist() == ol, (n, e, ply)
+            assert cnt[e] == len(ol)
+            m = np.zeros(n * n, dtype=np.uint8)
+            m[ol] = 1
+            assert np.array_equal(mask[e], m), (n, e, ply)
+            assert int(player[e]) == st.current_player(), (n, e, ply)
+            assert bool(term[e]) == st.is_terminal()
+            assert rets[e].tolist() == st.returns()
+            assert np.array_equal(recs[e], st.export_record()), (n, e, ply)
+            if obs is not None:
+                assert np.array_equal(obs[e].reshape(-1), st.observation_tensor(0)), (n, e, ply)
+        if ply == maxlen:
+            break
+        step = acts[:, ply].copy()
+        status = batch.apply(step)
+        for e, st in enumerate(states):
+            if step[e] >= 0:
+                assert status[e] == 0
+                st.apply_action(int(step[e]))
+            else:
+                assert status[e] == 2
+    batch.close()
+
+
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 19, 23, 24])
+def test_lockstep_random_games(oracle_mod, n):
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(1000 + n)
+    num = 96 if n <= 12 else 40
+    games = [random_game_actions(og, rng, force_swap=(i % 3 == 0)) for i in range(num)]
+    _lockstep(oracle_mod, n, games, check_obs_every=1 if n <= 12 else 9)
+
+
+def test_lockstep_draw_seeking_n5(oracle_mod):
+    og = oracle_mod.OracleGame(5)
+    games = [draw_seeking_actions(og, p) for p in [(0, 1), (0, 0), (10**6, 10**6), (1, 0), (2, 3), (0, 10**6)]]
+    assert games[0] == [5, 2, 6, 3, 7, 8, 9, 11, 10, 12, 13, 16, 14, 17, 15, 18, 19, 21]
+    _lockstep(oracle_mod, 5, games)
+
+
+def test_n5_all_first_moves_with_and_without_swap(oracle_mod):
+    """BASELINE config C2: every first move x {swap where legal, two other replies} x random continuations."""
+    og = oracle_mod.OracleGame(5)
+    rng = random.Random(5)
+    games = []
+    first_moves = og.new_initial_state().legal_actions()
+    assert len(first_moves) == 15
+    for f in first_moves:
+        st = og.new_initial_state()
+        st.apply_action(f)
+        replies = st.legal_actions()
+        picks = ([f] if f in replies else []) + rng.sample([a for a in replies if a != f], 2)
+        for r in picks:
+            for _ in range(6):
+                s2 = st.clone()
+                s2.apply_action(r)
+                g = [f, r]
+                while not s2.is_terminal():
+                    a = rng.choice(s2.legal_actions())
+                    s2.apply_action(a)
+                    g.append(a)
+                games.append(g)
+    _lockstep(oracle_mod, 5, games)
+
+
+def test_illegal_actions_leave_state_untouched(oracle_mod):
+    from twixt_for_open_spiel_b200 import SpielFatalError, TwixTBatch
+    n = 8
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(77)
+    E = 64
+    batch = TwixTBatch(n, E, 0, SEED)
+    states = [og.new_initial_state() for _ in range(E)]
+    for ply in range(40):
+        acts = np.zeros(E, dtype=np.int32)
+        legal_flags = []
+        for e, st in enumerate(states):
+            la = st.legal_actions()
+            if st.is_terminal() or rng.random() < 0.3:
+                a = rng.randrange(0, n * n + 5)  # may be legal by chance; may be out of range
+            else:
+                a = rng.choice(la)
+            acts[e] = a
+            legal_flags.append(a in la)
+        before = batch.export_state()
+        status = batch.apply(acts, raise_on_illegal=False)
+        after = batch.export_state()
+        first_bad = None
+        for e, st in enumerate(states):
+            if legal_flags[e]:
+                assert status[e] == 0
+                st.apply_action(int(acts[e]))
+            else:
+                assert status[e] == 1
+                assert np.array_equal(before[e], after[e])
+                if first_bad is None:
+                    first_bad = int(acts[e])
+            assert np.array_equal(after[e], st.export_record())
+        if first_bad is not None:  # the reference's message, twixt.h:96
+            snapshot = batch.export_state()
+            with pytest.raises(SpielFatalError, match=r"^Not a legal action: %d$" % first_bad):
+                bad_only = np.where(np.array(legal_flags), -1, acts).astype(np.int32)
+                batch.apply(bad_only)
+            assert np.array_equal(snapshot, batch.export_state())
+    batch.close()
+
+
+def test_device_pointer_path_matches_host_path(oracle_mod):
+    """Outputs written straight into torch CUDA tensors equal the staged host outputs."""
+    import torch
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    n = 12
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(3)
+    games = [random_game_actions(og, rng, force_swap=(i % 2 == 0), max_plies=30 + i % 20) for i in range(50)]
+    E = len(games)
+    batch = TwixTBatch(n, E, 0, SEED)
+    acts = pad_games(games)
+    dev = torch.device("cuda:0")
+    for ply in range(acts.shape[1]):
+        a_dev = torch.from_numpy(acts[:, ply].copy()).to(dev)
+        st_dev = torch.full((E,), 9, dtype=torch.int32, device=dev)
+        batch.apply(a_dev, out_status=st_dev)
+    batch.synchronize()
+    la_h, cnt_h = batch.legal_actions()
+    la_d = torch.full((E, batch.max_legal_actions), -1, dtype=torch.int64, device=dev)
+    cnt_d = torch.zeros(E, dtype=torch.int32, device=dev)
+    batch.legal_actions(out_actions=la_d, out_counts=cnt_d)
+    la16_d = torch.zeros((E, batch.max_legal_actions), dtype=torch.int16, device=dev)
+    batch.legal_actions(out_actions=la16_d, out_counts=cnt_d)
+    mask_d = torch.zeros((E, n * n), dtype=torch.uint8, device=dev)
+    batch.legal_mask(out=mask_d)
+    obs_d = torch.empty((E,) + batch.obs_shape, dtype=torch.float32, device=dev)
+    batch.observation(out=obs_d)
+    ret_d = torch.zeros((E, 2), dtype=torch.float32, device=dev)
+    batch.returns(out=ret_d)
+    batch.synchronize()
+    assert np.array_equal(cnt_d.cpu().numpy(), cnt_h)
+    for e in range(E):
+        assert np.array_equal(la_d[e, :cnt_h[e]].cpu().numpy(), la_h[e, :cnt_h[e]])
+        assert np.array_equal(la16_d[e, :cnt_h[e]].cpu().numpy().astype(np.int64), la_h[e, :cnt_h[e]])
+    assert np.array_equal(mask_d.cpu().numpy(), batch.legal_mask())
+    assert np.array_equal(obs_d.cpu().numpy(), batch.observation())
+    assert np.array_equal(ret_d.cpu().numpy(), batch.returns())
+    # unaligned float output takes the scalar-store kernel
+    raw = torch.empty(E * batch.info.obs_size + 1, dtype=torch.float32, device=dev)
+    batch.observation(out=raw[1:])
+    batch.synchronize()
+    assert np.array_equal(raw[1:].cpu().numpy().reshape(obs_d.shape), obs_d.cpu().numpy())
+    batch.close()
+
+
+@pytest.mark.parametrize("n", [5, 8, 12, 17, 24])
+def test_fused_playout_replays_on_oracle(oracle_mod, n):
+    """K5: every game the fused kernel plays is regenerated move for move by the oracle's
+    restatement of the Philox policy; final records, returns and lengths agree."""
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    og = oracle_mod.OracleGame(n)
+    E = 300 if n <= 12 else 160
+    batch = TwixTBatch(n, E, 0, SEED)
+    batch.set_stream_base(1 << 20)
+    rets, lens, trace = batch.playout(trace=True)
+    recs = batch.export_state()
+    stats = batch.stats()
+    assert stats["games"] == E and stats["plies"] == int(lens.sum())
+    assert stats["red_wins"] + stats["blue_wins"] + stats["draws"] == E
+    assert bool(batch.is_terminal().all())
+    for e in range(E):
+        st = og.new_initial_state()
+        oa = st.playout_philox(SEED, (1 << 20) + e)
+        assert lens[e] == len(oa), (n, e)
+        assert trace[:lens[e], e].tolist() == oa, (n, e)
+        assert (trace[lens[e]:, e] == 0xFFFF).all()
+        assert rets[e].tolist() == st.returns()
+        assert np.array_equal(recs[e], st.export_record()), (n, e)
+    assert stats["max_length"] == int(lens.max())
+    batch.close()
+
+
+def test_playout_from_midgame_clones_with_stream_ids(oracle_mod):
+    """BASELINE config C3 shape: leaves cloned x4, rolled out with explicit stream ids and a ply budget."""
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    n = 12
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(12)
+    B, R = 48, 4
+    batch = TwixTBatch(n, B + B * R, 0, SEED)
+    leaves, games = [], []
+    for i in range(B):
+        g = random_game_actions(og, rng, force_swap=(i % 4 == 0), max_plies=rng.randrange(0, 61))
+        st = og.new_initial_state()
+        st.replay(g)
+        leaves.append(st)
+        games.append(g)
+    acts = pad_games(games)
+    for ply in range(acts.shape[1]):
+        batch.apply(acts[:, ply].copy(), 0)
+    src = np.repeat(np.arange(B, dtype=np.int64), R)
+    batch.clone_gather(src, B)
+    ids = (np.arange(B * R, dtype=np.uint64) * np.uint64(7919)) + np.uint64(5)
+    budget = 25
+    rets, lens, trace = batch.playout(B, B * R, max_plies=budget, stream_ids=ids, trace=True)
+    recs = batch.export_state(B, B * R)
+    leaf_recs = batch.export_state(0, B)
+    for i in range(B):
+        assert np.array_equal(leaf_recs[i], leaves[i].export_record())  # sources untouched
+    for j in range(B * R):
+        st = leaves[j // R].clone()
+        oa = st.playout_philox(SEED, int(ids[j]), budget)
+        assert lens[j] == len(oa)
+        assert trace[:lens[j], j].tolist() == oa
+        assert np.array_equal(recs[j], st.export_record())
+        assert rets[j].tolist() == st.returns()
+    batch.close()
+
+
+def test_reset_clone_import_roundtrip(oracle_mod):
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    n = 9
+    batch = TwixTBatch(n, 64, 0, SEED)
+    batch.playout(0, 32, max_plies=17)
+    a = batch.export_state(0, 32)
+    batch.clone(0, 32, 32)
+    assert np.array_equal(batch.export_state(32, 32), a)
+    batch.reset(0, 32)
+    init = oracle_mod.OracleGame(n).new_initial_state().export_record()
+    assert all(np.array_equal(r, init) for r in batch.export_state(0, 32))
+    batch.import_state(a, 0)
+    assert np.array_equal(batch.export_state(0, 32), a)
+    other = TwixTBatch(n, 8, 0, 1)
+    other.clone_from(0, batch, 5, 8)
+    assert np.array_equal(other.export_state(), a[5:13])
+    with pytest.raises(ValueError):
+        batch.clone(0, 10, 20)  # overlap
+    with pytest.raises(ValueError):
+        batch.reset(60, 10)  # out of range
+    other.close()
+    batch.close()
+
+
+def test_spiel_adapter_reference_kats():
+    """The reference's own tests (twixt_test.cc:108-199) re-hosted on the adapter."""
+    from twixt_for_open_spiel_b200 import SpielFatalError, load_game
+    game = load_game("twixt")
+    st = game.new_initial_state()
+    assert st.current_player() == 0 and 11 in st.legal_actions()
+    st.apply_action(19)
+    assert st.current_player() == 1
+    st.apply_action(19)  # swap
+    assert 19 in st.legal_actions() and 29 not in st.legal_actions()
+    assert st.current_player() == 0
+    st.apply_action(36)
+    la = st.legal_actions()
+    assert 19 in la and 29 not in la and 36 not in la
+
+    st = game.new_initial_state()
+    assert not st.is_terminal() and len(st.legal_actions()) == 48
+    sizes = []
+    for a in [21, 38, 15, 11]:
+        st.apply_action(a)
+        sizes.append(len(st.legal_actions()))
+    assert sizes == [48, 46, 46, 44]
+    with pytest.raises(SpielFatalError, match=r"^Not a legal action: 11$"):
+        st.apply_action(11)
+    for a, want in [(27, 44), (17, 42), (42, 42), (45, 40)]:
+        st.apply_action(a)
+        assert len(st.legal_actions()) == want
+    c = st.clone()
+    st.apply_action(48)
+    assert st.is_terminal() and st.player_return(0) == 1.0 and st.player_return(1) == -1.0
+    assert st.current_player() == -4 and st.legal_actions() == []
+    assert not c.is_terminal() and len(c.legal_actions()) == 40  # clone is independent
+
+    g5 = load_game("twixt(board_size=5)")
+    st = g5.new_initial_state()
+    while not st.is_terminal():
+        st.apply_action(st.legal_actions()[0])
+        st.apply_action(st.legal_actions()[1])
+    assert st.returns() == [0.0, 0.0]
+    assert st.history() == [5, 2, 6, 3, 7, 8, 9, 11, 10, 12, 13, 16, 14, 17, 15, 18, 19, 21]

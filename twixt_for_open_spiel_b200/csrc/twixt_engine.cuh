@@ -1,0 +1,399 @@
+// twixt_engine.cuh -- the per-env TwixT rules on the bit-plane state record.
+//
+// One game ("env") is a record of 4 header words + 9 bit-planes of n column
+// words (layout: include/twixt_b200.h).  Everything here is scalar code for
+// ONE env, templated on a memory accessor so the same rules run
+//   * thread-per-env on the record in global memory      (apply kernel),
+//   * thread-per-env on a record staged in shared memory (fused playout),
+// and -- compiled for the host by tests/host_engine_harness.cc only -- on a
+// plain array, so the rules can be checked against the oracle without a GPU.
+// The product library never runs this on the CPU.
+//
+// Reference semantics reproduced (file:line under
+// /root/reference/open_spiel/games/twixt/):
+//   legal lists + swap quirk   twixtboard.cc:252-276, 457-493, 633-640
+//   peg, links, crossings      twixtboard.cc:501-556, 38-144, 176-190
+//   border flags + flood       twixtboard.cc:537-546, 557-588
+//   result                     twixtboard.cc:192-207
+//   observation planes         twixt.cc:76-132, twixtboard.cc:590-597
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TW_HD __host__ __device__ __forceinline__
+#define TW_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define TW_HD inline
+#define TW_HD_NOINLINE inline
+#endif
+
+namespace twixt {
+
+enum : int { P_RED = 0, P_BLUE = 1, P_LINK0 = 2, P_BLOCKED = 6, P_START = 7, P_END = 8, kNumStatePlanes = 9 };
+enum : int { kHeaderWords = 4 };
+enum : int { kOpen = 0, kRedWin = 1, kBlueWin = 2, kDraw = 3 };
+enum : int { kRed = 0, kBlue = 1 };
+enum : int { kTerminalPlayer = -4 };
+enum : uint32_t { kNoMove = 0xFFFFFFFFu };
+
+TW_HD int record_words(int n) { return (kHeaderWords + kNumStatePlanes * n + 3) & ~3; }
+
+TW_HD int tw_popc(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+// index of the lowest set bit, v != 0
+TW_HD int tw_ctz(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs(static_cast<int>(v)) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+// Compass offsets (twixtcell.h:58-68), biased by +2 and packed one nibble per
+// direction so a lookup is a shift and a mask.
+TW_HD int dir_dx(int d) { return static_cast<int>((0x10013443u >> (4 * d)) & 15u) - 2; }
+TW_HD int dir_dy(int d) { return static_cast<int>((0x43100134u >> (4 * d)) & 15u) - 2; }
+
+struct Header {
+  uint32_t ply;       // Board::move_counter_
+  uint32_t result;    // kOpen..kDraw
+  uint32_t swapped;   // 0/1
+  uint32_t move_one;  // action of the first move or kNoMove
+  int cnt[2];         // empty cells red / blue may play on
+};
+
+TW_HD void unpack_header(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, Header& h) {
+  h.ply = w0;
+  h.result = w1 & 3u;
+  h.swapped = (w1 >> 2) & 1u;
+  h.move_one = w2;
+  h.cnt[0] = static_cast<int>(w3 & 0xFFFFu);
+  h.cnt[1] = static_cast<int>(w3 >> 16);
+}
+TW_HD void pack_header(const Header& h, uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  w0 = h.ply;
+  w1 = h.result | (h.swapped << 2);
+  w2 = h.move_one;
+  w3 = static_cast<uint32_t>(h.cnt[0]) | (static_cast<uint32_t>(h.cnt[1]) << 16);
+}
+
+// Accessor over a record whose words are `stride` words apart (1 for a record
+// in global memory, the number of threads sharing the staging buffer for a
+// record transposed into shared memory).
+// kN > 0 fixes the board size at compile time (fused playout), kN == 0 reads it
+// from n_rt.
+template <int kStride, int kN = 0>
+struct RecordRef {
+  uint32_t* p;
+  int n_rt;
+  TW_HD int n() const { return kN > 0 ? kN : n_rt; }
+  TW_HD uint32_t word(int w) const { return p[w * kStride]; }
+  TW_HD void set_word(int w, uint32_t v) { p[w * kStride] = v; }
+  TW_HD uint32_t ld(int plane, int col) const { return p[(kHeaderWords + plane * n() + col) * kStride]; }
+  TW_HD void st(int plane, int col, uint32_t v) { p[(kHeaderWords + plane * n() + col) * kStride] = v; }
+  // column outside the board reads as empty
+  TW_HD uint32_t ld_guard(int plane, int col) const {
+    return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
+  }
+};
+
+template <class B>
+TW_HD void load_header(const B& b, Header& h) {
+  unpack_header(b.word(0), b.word(1), b.word(2), b.word(3), h);
+}
+template <class B>
+TW_HD void store_header(B& b, const Header& h) {
+  uint32_t w0, w1, w2, w3;
+  pack_header(h, w0, w1, w2, w3);
+  b.set_word(0, w0);
+  b.set_word(1, w1);
+  b.set_word(2, w2);
+  b.set_word(3, w3);
+}
+
+TW_HD uint32_t full_rows(int n) { return (1u << n) - 1u; }
+TW_HD uint32_t inner_rows(int n) { return ((1u << n) - 1u) & ~1u & ~(1u << (n - 1)); }
+
+// Cells `player` may ever play on in column x: red everything in columns
+// 1..n-2, blue rows 1..n-2 of every column (InitializeLegalActions,
+// twixtboard.cc:252-276; corners are off-board, 625-631).
+TW_HD uint32_t playable_word(int n, int player, int x) {
+  if (player == kRed) return (x >= 1 && x <= n - 2) ? full_rows(n) : 0u;
+  return inner_rows(n);
+}
+
+// The initial record of an env (Board::Board, twixtboard.cc:168-174).
+template <class B>
+TW_HD void init_record(B& b) {
+  int n = b.n();
+  int words = record_words(n);
+  for (int w = kHeaderWords; w < words; ++w) b.set_word(w, 0u);
+  Header h;
+  h.ply = 0; h.result = kOpen; h.swapped = 0; h.move_one = kNoMove;
+  h.cnt[0] = h.cnt[1] = n * (n - 2);
+  store_header(b, h);
+}
+
+TW_HD int current_player(const Header& h) {
+  return h.result != kOpen ? static_cast<int>(kTerminalPlayer) : static_cast<int>(h.ply & 1u);
+}
+
+// |LegalActions()| (twixt.h:86-90).  At ply 1 blue's list is still the initial
+// one -- the occupied first-move cell stays in it as the swap offer
+// (twixtboard.cc:485-488) -- from ply 2 on both lists are "playable and empty".
+TW_HD int legal_count(const Header& h, int n) {
+  if (h.result != kOpen) return 0;
+  if (h.ply == 1u) return n * (n - 2);
+  return h.cnt[h.ply & 1u];
+}
+
+// Legal cells of the player to move in column x (result must be open).
+template <class B>
+TW_HD uint32_t legal_word(const B& b, const Header& h, int x) {
+  int player = static_cast<int>(h.ply & 1u);
+  uint32_t play = playable_word(b.n(), player, x);
+  if (h.ply == 1u) return play;
+  return play & ~(b.ld(P_RED, x) | b.ld(P_BLUE, x));
+}
+
+template <class B>
+TW_HD bool is_legal(const B& b, const Header& h, int action) {
+  int n = b.n();
+  if (h.result != kOpen) return false;
+  if (action < 0 || action >= n * n) return false;
+  int x = action / n, y = action - x * n;
+  return (legal_word(b, h, x) >> y) & 1u;
+}
+
+// Is the link (wx,wy) -> east direction de crossed by any existing link, of
+// either colour (twixtboard.cc:519-527 tests HasLink only)?
+template <class B>
+TW_HD bool crossing_blocked(const B& b, int wx, int wy, int de) {
+#define TW_X(plane, ox, mask) (b.ld_guard(P_LINK0 + (plane), wx + (ox)) & ((static_cast<uint32_t>(mask) << wy) >> 3))
+#define TW_CROSS_CASE(d, expr) \
+  case d:                      \
+    return (expr) != 0u;
+  switch (de) {
+#include "twixt_crossing.inc"
+  }
+#undef TW_CROSS_CASE
+#undef TW_X
+  return false;
+}
+
+// Cell::links_ of (x,y) reassembled from the four west-endpoint planes.
+template <class B>
+TW_HD uint32_t links_of(const B& b, int x, int y) {
+  uint32_t m = 0;
+  m |= ((b.ld(P_LINK0 + 0, x) >> y) & 1u) << 0;
+  m |= ((b.ld(P_LINK0 + 1, x) >> y) & 1u) << 1;
+  m |= ((b.ld(P_LINK0 + 2, x) >> y) & 1u) << 2;
+  m |= ((b.ld(P_LINK0 + 3, x) >> y) & 1u) << 3;
+  m |= (((b.ld_guard(P_LINK0 + 0, x - 1) << 2) >> y) & 1u) << 4;  // SSW: NNE link of (x-1,y-2)
+  m |= (((b.ld_guard(P_LINK0 + 1, x - 2) << 1) >> y) & 1u) << 5;  // WSW: ENE link of (x-2,y-1)
+  m |= ((b.ld_guard(P_LINK0 + 2, x - 2) >> (y + 1)) & 1u) << 6;   // WNW: ESE link of (x-2,y+1)
+  m |= ((b.ld_guard(P_LINK0 + 3, x - 1) >> (y + 2)) & 1u) << 7;   // NNW: SSE link of (x-1,y+2)
+  return m;
+}
+
+// ExploreLocalGraph (twixtboard.cc:573-588): give `flag_plane` to every cell
+// reachable from (x,y) through links over cells that lack it.  Depth-first
+// with a small explicit stack; if the stack overflows the dropped cells are
+// recovered by closing the flagged set under the link relation (rare).
+template <int kStack, class B>
+TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y) {
+  uint16_t stack[kStack];
+  int sp = 0;
+  bool overflow = false;
+  stack[sp++] = static_cast<uint16_t>((x << 8) | y);
+  while (sp > 0) {
+    uint32_t c = stack[--sp];
+    int cx = static_cast<int>(c >> 8), cy = static_cast<int>(c & 255u);
+    uint32_t lm = links_of(b, cx, cy);
+    while (lm) {
+      int d = tw_ctz(lm);
+      lm &= lm - 1u;
+      int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
+      uint32_t f = b.ld(flag_plane, tx);
+      if (!((f >> ty) & 1u)) {
+        b.st(flag_plane, tx, f | (1u << ty));
+        if (sp < kStack) stack[sp++] = static_cast<uint16_t>((tx << 8) | ty);
+        else overflow = true;
+      }
+    }
+  }
+  if (overflow) {
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (int cx = 0; cx < b.n(); ++cx) {
+        uint32_t w = b.ld(flag_plane, cx) & b.ld(own_plane, cx);
+        while (w) {
+          int cy = tw_ctz(w);
+          w &= w - 1u;
+          uint32_t lm = links_of(b, cx, cy);
+          while (lm) {
+            int d = tw_ctz(lm);
+            lm &= lm - 1u;
+            int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
+            uint32_t f = b.ld(flag_plane, tx);
+            if (!((f >> ty) & 1u)) {
+              b.st(flag_plane, tx, f | (1u << ty));
+              changed = true;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// SetPegAndLinks (twixtboard.cc:501-571) for a peg of `player` on the empty
+// cell (x,y).  Returns true iff the new peg is now linked to both of its
+// owner's border lines (the win test of UpdateResult, twixtboard.cc:194-199).
+template <int kStack, class B>
+TW_HD bool set_peg_and_links(B& b, Header& h, int player, int x, int y) {
+  const int n = b.n();
+  const int own = player == kRed ? P_RED : P_BLUE;
+  const uint32_t bit = 1u << y;
+  b.st(own, x, b.ld(own, x) | bit);
+  h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
+  h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
+
+  // border flags the cell has by position (twixtboard.cc:223-231); a peg can
+  // only stand on its owner's border lines
+  bool to_start = player == kRed ? (y == 0) : (x == 0);
+  bool to_end = player == kRed ? (y == n - 1) : (x == n - 1);
+  bool neutral = false, new_links = false;
+
+  // own-colour pegs a knight's move away, as a Compass-ordered 8-bit mask
+  const uint32_t e1 = b.ld_guard(own, x + 1), e2 = b.ld_guard(own, x + 2);
+  const uint32_t w1 = b.ld_guard(own, x - 1), w2 = b.ld_guard(own, x - 2);
+  uint32_t cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
+                  ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) |
+                  ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) | (((w1 >> (y + 2)) & 1u) << 7);
+  while (cand) {
+    const int d = tw_ctz(cand);
+    cand &= cand - 1u;
+    const int tx = x + dir_dx(d), ty = y + dir_dy(d);
+    // the link named by its west endpoint and east direction
+    const int wx = d < 4 ? x : tx, wy = d < 4 ? y : ty, de = d & 3;
+    if (crossing_blocked(b, wx, wy, de)) {
+      // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
+      // pointing east is ever read (twixtcell.h:82-84) and it always lands on
+      // the west endpoint
+      b.st(P_BLOCKED, wx, b.ld(P_BLOCKED, wx) | (1u << wy));
+    } else {
+      b.st(P_LINK0 + de, wx, b.ld(P_LINK0 + de, wx) | (1u << wy));
+      new_links = true;
+      if ((b.ld(P_START, tx) >> ty) & 1u) to_start = true;       // twixtboard.cc:538-540
+      else if ((b.ld(P_END, tx) >> ty) & 1u) to_end = true;      // 541-543
+      else neutral = true;                                       // 544-546
+    }
+  }
+  if (to_start) b.st(P_START, x, b.ld(P_START, x) | bit);
+  if (to_end) b.st(P_END, x, b.ld(P_END, x) | bit);
+  if (new_links && neutral) {  // twixtboard.cc:558-570
+    if (to_start) flood_flag<kStack>(b, own, P_START, x, y);
+    if (to_end) flood_flag<kStack>(b, own, P_END, x, y);
+  }
+  return to_start && to_end;
+}
+
+// Board::ApplyAction (twixtboard.cc:457-499) for an action known to be legal,
+// given as its cell (x,y); action == x*n+y.
+template <int kStack, class B>
+TW_HD void apply_legal_cell(B& b, Header& h, int x, int y) {
+  const int n = b.n();
+  const int player = static_cast<int>(h.ply & 1u);
+  const uint32_t action = static_cast<uint32_t>(x * n + y);
+  if (h.ply == 1u && action == h.move_one) {
+    // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
+    // on the cell turned by 90 degrees (471-473)
+    b.st(P_RED, x, b.ld(P_RED, x) & ~(1u << y));
+    b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
+    b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
+    h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
+    h.cnt[kBlue] += (y >= 1 && y <= n - 2) ? 1 : 0;
+    h.swapped = 1u;
+    const int rx = y, ry = n - 1 - x;
+    x = rx;
+    y = ry;
+  }
+  const bool win = set_peg_and_links<kStack>(b, h, player, x, y);
+  if (h.ply == 0u) h.move_one = action;
+  h.ply += 1u;
+  if (win) h.result = player == kRed ? kRedWin : kBlueWin;     // twixtboard.cc:194-199
+  else if (h.cnt[1 - player] == 0) h.result = kDraw;           // 203-206
+}
+
+// Position of the k-th (0-based) set bit of w; k < popc(w).
+TW_HD int select_bit(uint32_t w, int k) {
+  int pos = 0, c;
+  c = tw_popc(w & 0xFFFFu);
+  if (k >= c) { k -= c; pos += 16; w >>= 16; }
+  c = tw_popc(w & 0xFFu);
+  if (k >= c) { k -= c; pos += 8; w >>= 8; }
+  c = tw_popc(w & 0xFu);
+  if (k >= c) { k -= c; pos += 4; w >>= 4; }
+  c = tw_popc(w & 0x3u);
+  if (k >= c) { k -= c; pos += 2; w >>= 2; }
+  c = static_cast<int>(w & 1u);
+  if (k >= c) pos += 1;
+  return pos;
+}
+
+// The k-th action (0-based) of the ascending legal list, as a cell; k <
+// legal_count.  Ascending action order is column-major (action = x*n+y,
+// twixtboard.cc:603-605), i.e. the order of the column words.
+template <class B>
+TW_HD void select_legal(const B& b, const Header& h, int k, int& out_x, int& out_y) {
+  int sx = 0, sk = 0;
+  uint32_t sw = 0;
+  for (int x = 0; x < b.n(); ++x) {
+    uint32_t w = legal_word(b, h, x);
+    if (k >= 0) { sx = x; sw = w; sk = k; }
+    k -= tw_popc(w);
+  }
+  out_x = sx;
+  out_y = select_bit(sw, sk);
+}
+
+// Column word of "peg has at least one link" (Cell::HasLinks, twixtcell.h:78).
+template <class B>
+TW_HD uint32_t haslink_word(const B& b, int x) {
+  uint32_t m = b.ld(P_LINK0 + 0, x) | b.ld(P_LINK0 + 1, x) | b.ld(P_LINK0 + 2, x) | b.ld(P_LINK0 + 3, x);
+  m |= b.ld_guard(P_LINK0 + 0, x - 1) << 2;
+  m |= b.ld_guard(P_LINK0 + 1, x - 2) << 1;
+  m |= b.ld_guard(P_LINK0 + 2, x - 2) >> 1;
+  m |= b.ld_guard(P_LINK0 + 3, x - 1) >> 2;
+  return m;
+}
+
+// Column word (over y) of observation plane `plane` (0..11) in BOARD
+// coordinates: which cells (x, .) put a 1.0 into that plane
+// (SetPegAndLinksOnTensor, twixt.cc:76-99).
+template <class B>
+TW_HD uint32_t obs_plane_word(const B& b, int plane, int x) {
+  const int own = plane < 6 ? P_RED : P_BLUE;
+  const int k = plane < 6 ? plane : plane - 6;
+  const uint32_t pegs = b.ld(own, x);
+  if (k == 0) return pegs & ~haslink_word(b, x);
+  if (k == 5) return pegs & b.ld(P_BLOCKED, x);
+  return pegs & b.ld(P_LINK0 + (k - 1), x);
+}
+
+// Board cell feeding tensor element (plane, r, c) (GetTensorPosition,
+// twixtboard.cc:590-597, inverted): red planes are the board seen from above
+// without red's... opponent's end columns, blue planes are turned by 90 degrees.
+TW_HD void obs_cell(int n, int plane, int r, int c, int& x, int& y) {
+  if (plane < 6) { x = c + 1; y = n - 1 - r; }
+  else { x = n - 1 - r; y = n - 2 - c; }
+}
+
+}  // namespace twixt
