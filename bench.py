@@ -258,6 +258,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from twixt_for_open_spiel_b200 import TwixTBatch
+    from twixt_for_open_spiel_b200.sharding import reduce_counters, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -278,7 +279,8 @@ def run_ours(args):
     n, E = args.board_size, args.envs
     batch = TwixTBatch(n, E, local, SEED)
     batch.use_torch_stream()
-    batch.set_stream_base(rank * E)  # global env ids: shard r owns [r*E, (r+1)*E)
+    first_id, _ = shard_range(E * world, world, rank)  # weak scaling: E envs per GPU
+    batch.set_stream_base(first_id)  # global env ids: shard r owns [r*E, (r+1)*E)
     rets = torch.zeros((E, 2), dtype=torch.float32, device=dev)
     lens = torch.zeros(E, dtype=torch.int32, device=dev)
 
@@ -312,15 +314,12 @@ def run_ours(args):
     launches = st["kernel_launches"] - launches0
     kernel_ms = [s.elapsed_time(e) for s, e in k_evs]
 
-    red = torch.tensor([st["plies"], st["games"], st["red_wins"], st["blue_wins"], st["draws"], st["swaps"]],
-                       dtype=torch.int64, device=dev)
+    tot = reduce_counters(st, dist if world > 1 else None, dev)  # the only collective of the whole job
     tmax = torch.tensor([elapsed_ms, sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
-    mx = torch.tensor([st["max_length"]], dtype=torch.int64, device=dev)
-    if world > 1:  # the only collective of the whole job: a handful of counters
-        dist.all_reduce(red, op=dist.ReduceOp.SUM)
+    if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    total_plies = int(red[0].item())
+    red = [tot["plies"], tot["games"], tot["red_wins"], tot["blue_wins"], tot["draws"], tot["swaps"]]
+    total_plies = int(red[0])
     elapsed_s = float(tmax[0].item()) * 1e-3
     value = total_plies / elapsed_s
 
@@ -387,7 +386,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "outcomes": {"plies": total_plies, "games": int(red[1]), "red": int(red[2]), "blue": int(red[3]),
-                         "draws": int(red[4]), "swaps": int(red[5]), "max_length": int(mx.item())},
+                         "draws": int(red[4]), "swaps": int(red[5]), "max_length": int(tot["max_length"])},
         }
         if world == 1 and not args.no_cpu:
             v, kind, cores, detail = cpu_reference(n, args.cpu_seconds)

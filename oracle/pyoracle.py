@@ -144,6 +144,8 @@ def ref_lib() -> C.CDLL:
         lib.ref_export_cells.argtypes = [C.c_void_p, C.c_void_p]
         lib.ref_replay.restype = C.c_int
         lib.ref_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.ref_blockers.restype = C.c_int
+        lib.ref_blockers.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         lib.ref_playout_philox.restype = C.c_int
         lib.ref_playout_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _ref_lib = lib
@@ -307,6 +309,12 @@ class RefGame:
 
     def new_initial_state(self) -> "RefState":
         return RefState(self, self.lib.ref_state_new(self.h))
+
+    def blockers(self, x: int, y: int, d: int):
+        """BlockerMap entries of link (x,y,d); valid only after a state of this size was constructed."""
+        out = np.zeros(3 * 32, dtype=np.int32)
+        c = self.lib.ref_blockers(x, y, d, _ptr(out), 32)
+        return [tuple(int(v) for v in out[3 * i:3 * i + 3]) for i in range(c)]
 
 
 class RefState(_StateBase):

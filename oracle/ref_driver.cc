@@ -204,6 +204,26 @@ void ref_export_cells(void* s, int* out) {
   }
 }
 
+// The reference's crossing relation for the directed link (x,y,dir) of the board
+// size most recently constructed (BlockerMap is process-global,
+// twixtboard.h:142-151): triples (x,y,dir), both encodings of every crosser.
+int ref_blockers(int x, int y, int dir, int* out, int cap) {
+  Link link;
+  link.position = {x, y};
+  link.direction = dir;
+  const std::set<Link>& bl = open_spiel::twixt::BlockerMap::GetBlockers(link);
+  int i = 0;
+  for (const Link& b : bl) {
+    if (i < cap) {
+      out[3 * i + 0] = b.position.x;
+      out[3 * i + 1] = b.position.y;
+      out[3 * i + 2] = b.direction;
+    }
+    ++i;
+  }
+  return i;
+}
+
 // Both maintained legal lists (not only the mover's): player p's list.
 int ref_legal_list_of(void* s, int player, int64_t* out, int cap) {
   std::vector<Action> v = AsState(s)->board_.GetLegalActions(player);

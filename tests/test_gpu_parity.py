@@ -315,3 +315,65 @@ def test_spiel_adapter_reference_kats():
         st.apply_action(st.legal_actions()[1])
     assert st.returns() == [0.0, 0.0]
     assert st.history() == [5, 2, 6, 3, 7, 8, 9, 11, 10, 12, 13, 16, 14, 17, 15, 18, 19, 21]
+
+
+def test_cuda_matches_reference_generated_fixture():
+    """tests/golden/ref_games.json (outputs of the unmodified reference) replayed through the C ABI."""
+    import json
+    import os
+    import zlib
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_games.json")) as f:
+        games = json.load(f)["games"]
+    by_n = {}
+    for g in games:
+        by_n.setdefault(g["n"], []).append(g)
+    for n, gs in by_n.items():
+        batch = TwixTBatch(n, len(gs), 0, SEED)
+        acts = pad_games([g["actions"] for g in gs])
+        for ply in range(acts.shape[1] + 1):
+            la, cnt = batch.legal_actions()
+            player = batch.current_player()
+            obs = batch.observation()
+            for e, g in enumerate(gs):
+                if ply >= len(g["plies"]):
+                    continue
+                p, count, crc_l, crc_o = g["plies"][ply]
+                assert int(player[e]) == p and int(cnt[e]) == count, (n, e, ply)
+                assert (zlib.crc32(la[e, :count].astype(np.int64).tobytes()) & 0xFFFFFFFF) == crc_l
+                assert (zlib.crc32(obs[e].tobytes()) & 0xFFFFFFFF) == crc_o, (n, e, ply)
+            if ply < acts.shape[1]:
+                batch.apply(acts[:, ply].copy())
+        rets, term = batch.returns(), batch.is_terminal()
+        for e, g in enumerate(gs):
+            assert bool(term[e]) == g["terminal"] and rets[e].tolist() == g["returns"]
+        batch.close()
+
+
+def test_cuda_golden_playthrough():
+    """The reference's playthrough.txt (committed as tests/golden/playthrough_n8.json) through the adapter."""
+    import json
+    import os
+    from twixt_for_open_spiel_b200 import load_game
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "playthrough_n8.json")) as f:
+        pt = json.load(f)
+    game = load_game("twixt")
+    assert game.num_distinct_actions() == 64 and game.max_game_length() == 61
+    assert game.observation_tensor_shape() == [12, 8, 6] and game.observation_tensor_size() == 576
+    st = game.new_initial_state()
+    by_index = {s["index"]: s for s in pt["states"]}
+    for ply in range(36):
+        s = by_index.get(ply)
+        if s is not None and "current_player" in s:
+            assert st.current_player() == s["current_player"] and st.is_terminal() == s["is_terminal"]
+            assert st.returns() == s["returns"] and st.history() == s["history"]
+            if "legal_actions" in s:
+                assert st.legal_actions() == s["legal_actions"]
+                assert [st.action_to_string(st.current_player(), a) for a in st.legal_actions()] == \
+                    s["string_legal_actions"]
+            for p in (0, 1):
+                if "obs_ones_%d" % p in s:
+                    assert np.flatnonzero(np.asarray(st.observation_tensor(p))).tolist() == s["obs_ones_%d" % p]
+        if ply < 35:
+            st.apply_action(pt["actions"][ply])
+    assert st.is_terminal() and st.returns() == [1.0, -1.0] and st.current_player() == -4
