@@ -40,10 +40,10 @@
  *      2..5 links NNE, ENE, ESE, SSE stored at their WEST endpoint
  *            (Cell::links_ bits 0..3 there, bits 4..7 at the other end,
  *             twixtcell.h:58-78)
- *      6 peg has a blocked neighbour in an east direction
- *            (Cell::HasBlockedNeighborsEast, twixtcell.h:82-84)
- *      7 / 8 peg is linked to its owner's start / end border line
+ *      6 / 7 peg is linked to its owner's start / end border line
  *            (Cell::linked_to_border_, twixtcell.h:89-95,107)
+ *      8 peg has a blocked neighbour in an east direction
+ *            (Cell::HasBlockedNeighborsEast, twixtcell.h:82-84)
  *    padding up to a multiple of 4 words.
  */
 #ifndef TWIXT_B200_H_

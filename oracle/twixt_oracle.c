@@ -381,8 +381,8 @@ int oracle_record_words(const oracle_game* g) {
 
 /* The packed record of include/twixt_b200.h, derived from the cell arrays.
  * planes: 0 red pegs, 1 blue pegs, 2..5 links NNE/ENE/ESE/SSE at the west
- * endpoint, 6 peg has a blocked neighbour in an east direction, 7/8 peg is
- * linked to its owner's start/end border line. */
+ * endpoint, 6/7 peg is linked to its owner's start/end border line, 8 peg has
+ * a blocked neighbour in an east direction. */
 void oracle_export_record(const oracle_game* g, const oracle_state* s, uint32_t* out) {
   int n = g->n;
   memset(out, 0, sizeof(uint32_t) * (size_t)oracle_record_words(g));
@@ -401,9 +401,9 @@ void oracle_export_record(const oracle_game* g, const oracle_state* s, uint32_t*
       pl[c * n + x] |= bit;
       for (int d = 0; d < 4; ++d)
         if ((s->links[x][y] >> d) & 1) pl[(2 + d) * n + x] |= bit;
-      if (s->blocked[x][y] & 15u) pl[6 * n + x] |= bit;
-      if (has_flag(s, x, y, c, START)) pl[7 * n + x] |= bit;
-      if (has_flag(s, x, y, c, END)) pl[8 * n + x] |= bit;
+      if (has_flag(s, x, y, c, START)) pl[6 * n + x] |= bit;
+      if (has_flag(s, x, y, c, END)) pl[7 * n + x] |= bit;
+      if (s->blocked[x][y] & 15u) pl[8 * n + x] |= bit;
     }
   out[0] = (uint32_t)s->move_counter;
   out[1] = (uint32_t)s->result | ((uint32_t)(s->swapped ? 1 : 0) << 2);

@@ -29,7 +29,7 @@
 
 namespace twixt {
 
-enum : int { P_RED = 0, P_BLUE = 1, P_LINK0 = 2, P_BLOCKED = 6, P_START = 7, P_END = 8, kNumStatePlanes = 9 };
+enum : int { P_RED = 0, P_BLUE = 1, P_LINK0 = 2, P_START = 6, P_END = 7, P_BLOCKED = 8, kNumStatePlanes = 9 };
 enum : int { kHeaderWords = 4 };
 enum : int { kOpen = 0, kRedWin = 1, kBlueWin = 2, kDraw = 3 };
 enum : int { kRed = 0, kBlue = 1 };
@@ -100,6 +100,22 @@ struct RecordRef {
   TW_HD uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
+  // the blocked plane is write-only for the rules (only ObservationTensor reads it)
+  TW_HD void or_blocked(int col, uint32_t bits) { st(P_BLOCKED, col, ld(P_BLOCKED, col) | bits); }
+};
+
+// Flood-fill work stack kept in a thread-local array (apply kernel, host tests).
+template <int kCap>
+struct LocalStack {
+  uint16_t v[kCap];
+  int sp = 0;
+  bool overflow = false;
+  TW_HD bool empty() const { return sp == 0; }
+  TW_HD void push(uint32_t c) {
+    if (sp < kCap) v[sp++] = static_cast<uint16_t>(c);
+    else overflow = true;
+  }
+  TW_HD uint32_t pop() { return v[--sp]; }
 };
 
 template <class B>
@@ -201,51 +217,56 @@ TW_HD uint32_t links_of(const B& b, int x, int y) {
   return m;
 }
 
-// ExploreLocalGraph (twixtboard.cc:573-588): give `flag_plane` to every cell
-// reachable from (x,y) through links over cells that lack it.  Depth-first
-// with a small explicit stack; if the stack overflows the dropped cells are
-// recovered by closing the flagged set under the link relation (rare).
-template <int kStack, class B>
-TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y) {
-  uint16_t stack[kStack];
-  int sp = 0;
-  bool overflow = false;
-  stack[sp++] = static_cast<uint16_t>((x << 8) | y);
-  while (sp > 0) {
-    uint32_t c = stack[--sp];
-    int cx = static_cast<int>(c >> 8), cy = static_cast<int>(c & 255u);
-    uint32_t lm = links_of(b, cx, cy);
-    while (lm) {
-      int d = tw_ctz(lm);
-      lm &= lm - 1u;
-      int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
-      uint32_t f = b.ld(flag_plane, tx);
+// ExploreLocalGraph (twixtboard.cc:573-588) gives a border flag to every cell
+// reachable from the new peg through links over cells that lack it.  It is
+// split into single VISITS so that the fused playout kernel can interleave the
+// visits of one env with the moves of the other envs of its warp instead of
+// making 31 lanes wait for one lane's whole flood.
+//
+// One visit: pop a cell, flag + push every linked neighbour that lacks the flag.
+template <class B, class Stack>
+TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
+  const uint32_t c = stk.pop();
+  const int cx = static_cast<int>(c >> 8), cy = static_cast<int>(c & 255u);
+  const uint32_t lm = links_of(b, cx, cy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int d = 0; d < 8; ++d) {
+    if ((lm >> d) & 1u) {
+      const int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
+      const uint32_t f = b.ld(flag_plane, tx);
       if (!((f >> ty) & 1u)) {
         b.st(flag_plane, tx, f | (1u << ty));
-        if (sp < kStack) stack[sp++] = static_cast<uint16_t>((tx << 8) | ty);
-        else overflow = true;
+        stk.push(static_cast<uint32_t>((tx << 8) | ty));
       }
     }
   }
-  if (overflow) {
-    bool changed = true;
-    while (changed) {
-      changed = false;
-      for (int cx = 0; cx < b.n(); ++cx) {
-        uint32_t w = b.ld(flag_plane, cx) & b.ld(own_plane, cx);
-        while (w) {
-          int cy = tw_ctz(w);
-          w &= w - 1u;
-          uint32_t lm = links_of(b, cx, cy);
-          while (lm) {
-            int d = tw_ctz(lm);
-            lm &= lm - 1u;
-            int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
-            uint32_t f = b.ld(flag_plane, tx);
-            if (!((f >> ty) & 1u)) {
-              b.st(flag_plane, tx, f | (1u << ty));
-              changed = true;
-            }
+}
+
+// If the stack overflowed, the dropped cells are recovered by closing the
+// flagged set of this colour under the link relation (flags are uniform per
+// connected component while a game is open, so this only grows the component
+// being flooded).  Rare; exercised by the tests with a 2-entry stack.
+template <class B>
+TW_HD_NOINLINE void flood_closure(B& b, int own_plane, int flag_plane) {
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (int cx = 0; cx < b.n(); ++cx) {
+      uint32_t w = b.ld(flag_plane, cx) & b.ld(own_plane, cx);
+      while (w) {
+        const int cy = tw_ctz(w);
+        w &= w - 1u;
+        uint32_t lm = links_of(b, cx, cy);
+        while (lm) {
+          const int d = tw_ctz(lm);
+          lm &= lm - 1u;
+          const int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
+          const uint32_t f = b.ld(flag_plane, tx);
+          if (!((f >> ty) & 1u)) {
+            b.st(flag_plane, tx, f | (1u << ty));
+            changed = true;
           }
         }
       }
@@ -253,11 +274,27 @@ TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y
   }
 }
 
-// SetPegAndLinks (twixtboard.cc:501-571) for a peg of `player` on the empty
-// cell (x,y).  Returns true iff the new peg is now linked to both of its
-// owner's border lines (the win test of UpdateResult, twixtboard.cc:194-199).
+// The whole flood at once (apply kernel, host tests).
 template <int kStack, class B>
-TW_HD bool set_peg_and_links(B& b, Header& h, int player, int x, int y) {
+TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y) {
+  LocalStack<kStack> stk;
+  stk.push(static_cast<uint32_t>((x << 8) | y));
+  while (!stk.empty()) flood_visit(b, flag_plane, stk);
+  if (stk.overflow) flood_closure(b, own_plane, flag_plane);
+}
+
+enum : uint32_t { kFloodStart = 1u, kFloodEnd = 2u };
+
+// SetPegAndLinks (twixtboard.cc:501-571) for a peg of `player` on the empty
+// cell (x,y), WITHOUT the flood: `pending` receives kFloodStart / kFloodEnd for
+// the floods the caller still has to run from (x,y) (twixtboard.cc:558-570).
+// Returns true iff the new peg is now linked to both of its owner's border
+// lines (the win test of UpdateResult, twixtboard.cc:194-199).
+// The eight directions are handled direction-major with compile-time offsets
+// and crossing masks, so lanes of a warp that link in the same direction stay
+// converged.
+template <class B>
+TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pending) {
   const int n = b.n();
   const int own = player == kRed ? P_RED : P_BLUE;
   const uint32_t bit = 1u << y;
@@ -274,41 +311,48 @@ TW_HD bool set_peg_and_links(B& b, Header& h, int player, int x, int y) {
   // own-colour pegs a knight's move away, as a Compass-ordered 8-bit mask
   const uint32_t e1 = b.ld_guard(own, x + 1), e2 = b.ld_guard(own, x + 2);
   const uint32_t w1 = b.ld_guard(own, x - 1), w2 = b.ld_guard(own, x - 2);
-  uint32_t cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
-                  ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) |
-                  ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) | (((w1 >> (y + 2)) & 1u) << 7);
-  while (cand) {
-    const int d = tw_ctz(cand);
-    cand &= cand - 1u;
-    const int tx = x + dir_dx(d), ty = y + dir_dy(d);
-    // the link named by its west endpoint and east direction
-    const int wx = d < 4 ? x : tx, wy = d < 4 ? y : ty, de = d & 3;
-    if (crossing_blocked(b, wx, wy, de)) {
-      // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
-      // pointing east is ever read (twixtcell.h:82-84) and it always lands on
-      // the west endpoint
-      b.st(P_BLOCKED, wx, b.ld(P_BLOCKED, wx) | (1u << wy));
-    } else {
-      b.st(P_LINK0 + de, wx, b.ld(P_LINK0 + de, wx) | (1u << wy));
-      new_links = true;
-      if ((b.ld(P_START, tx) >> ty) & 1u) to_start = true;       // twixtboard.cc:538-540
-      else if ((b.ld(P_END, tx) >> ty) & 1u) to_end = true;      // 541-543
-      else neutral = true;                                       // 544-546
+  const uint32_t cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
+                        ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) |
+                        ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) |
+                        (((w1 >> (y + 2)) & 1u) << 7);
+  if (cand) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int d = 0; d < 8; ++d) {
+      if ((cand >> d) & 1u) {
+        const int tx = x + dir_dx(d), ty = y + dir_dy(d);
+        // the link named by its west endpoint and east direction
+        const int wx = d < 4 ? x : tx, wy = d < 4 ? y : ty, de = d & 3;
+        if (crossing_blocked(b, wx, wy, de)) {
+          // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the
+          // bit pointing east is ever read (twixtcell.h:82-84) and it always
+          // lands on the west endpoint
+          b.or_blocked(wx, 1u << wy);
+        } else {
+          b.st(P_LINK0 + de, wx, b.ld(P_LINK0 + de, wx) | (1u << wy));
+          new_links = true;
+          if ((b.ld(P_START, tx) >> ty) & 1u) to_start = true;   // twixtboard.cc:538-540
+          else if ((b.ld(P_END, tx) >> ty) & 1u) to_end = true;  // 541-543
+          else neutral = true;                                   // 544-546
+        }
+      }
     }
   }
   if (to_start) b.st(P_START, x, b.ld(P_START, x) | bit);
   if (to_end) b.st(P_END, x, b.ld(P_END, x) | bit);
-  if (new_links && neutral) {  // twixtboard.cc:558-570
-    if (to_start) flood_flag<kStack>(b, own, P_START, x, y);
-    if (to_end) flood_flag<kStack>(b, own, P_END, x, y);
-  }
+  pending = (new_links && neutral) ? ((to_start ? kFloodStart : 0u) | (to_end ? kFloodEnd : 0u)) : 0u;
   return to_start && to_end;
 }
 
 // Board::ApplyAction (twixtboard.cc:457-499) for an action known to be legal,
-// given as its cell (x,y); action == x*n+y.
-template <int kStack, class B>
-TW_HD void apply_legal_cell(B& b, Header& h, int x, int y) {
+// given as its cell (x,y) (action == x*n+y), up to but excluding the border-
+// flag floods: on return (x,y) is the cell the peg went to (it differs from the
+// action's cell after a swap) and `pending` names the floods still to run from
+// it.  The result does not depend on them (the win test reads the new peg's
+// own flags), so the header is final.
+template <class B>
+TW_HD void apply_begin(B& b, Header& h, int& x, int& y, uint32_t& pending) {
   const int n = b.n();
   const int player = static_cast<int>(h.ply & 1u);
   const uint32_t action = static_cast<uint32_t>(x * n + y);
@@ -325,11 +369,23 @@ TW_HD void apply_legal_cell(B& b, Header& h, int x, int y) {
     x = rx;
     y = ry;
   }
-  const bool win = set_peg_and_links<kStack>(b, h, player, x, y);
+  const bool win = place_peg(b, h, player, x, y, pending);
   if (h.ply == 0u) h.move_one = action;
   h.ply += 1u;
   if (win) h.result = player == kRed ? kRedWin : kBlueWin;     // twixtboard.cc:194-199
   else if (h.cnt[1 - player] == 0) h.result = kDraw;           // 203-206
+}
+
+// The complete move (apply kernel, host tests).
+template <int kStack, class B>
+TW_HD void apply_legal_cell(B& b, Header& h, int x, int y) {
+  uint32_t pending;
+  apply_begin(b, h, x, y, pending);
+  if (pending) {
+    const int own = ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE;
+    if (pending & kFloodStart) flood_flag<kStack>(b, own, P_START, x, y);
+    if (pending & kFloodEnd) flood_flag<kStack>(b, own, P_END, x, y);
+  }
 }
 
 // Position of the k-th (0-based) set bit of w; k < popc(w).

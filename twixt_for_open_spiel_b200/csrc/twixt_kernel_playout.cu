@@ -1,17 +1,28 @@
 // twixt_kernel_playout.cu -- K5, the fused random-playout kernel.
 //
-// One THREAD per env.  Each warp copies the records of its 32 consecutive envs
-// from HBM into shared memory, transposed so that word w of lane l sits at
-// smem[w*32 + l]: whatever word each lane indexes, lane l always hits bank l,
-// so every access of the scalar rules in twixt_engine.cuh is conflict-free.
-// The whole game is then played out of shared memory -- select a uniformly
-// random legal action (Philox4x32-10, one block per four moves), apply it
-// (peg, links, crossing test, border flags, result) -- and the final records
-// are written back once.  HBM sees 2 x record bytes per GAME, not per move;
-// the limiter is issue slots and shared-memory latency, which is why the
-// thread-per-env mapping is used: it spends ~1/10 of the warp-instructions per
-// move of a warp-per-env mapping because nothing is computed redundantly
-// across lanes ("Mapping one game onto the machine").
+// One THREAD per env.  Each lane copies the bit-planes of its env from HBM into
+// shared memory, transposed so that word w of lane l sits at smem[w*32 + l]:
+// whatever word each lane indexes, lane l always hits bank l, so every access
+// of the scalar rules in twixt_engine.cuh is conflict-free.  The whole game is
+// then played out of shared memory -- select a uniformly random legal action
+// (Philox4x32-10, one block per four moves), apply it (peg, links, crossing
+// test, border flags, result) -- and the final planes are written back once.
+// HBM sees 2 x record bytes per GAME, not per move; the limiter is issue slots
+// and shared-memory latency, which is why the thread-per-env mapping is used:
+// it spends ~1/10 of the warp-instructions per move of a warp-per-env mapping
+// because nothing is computed redundantly across lanes ("Mapping
+// one game onto the machine").
+//
+// Divergence control (profiles/r1_playout_v1_*: 9.5 of 32 lanes active):
+//  * the border-flag flood (ExploreLocalGraph) is cut into single visits that
+//    are interleaved with the other lanes' moves: every loop iteration runs
+//    one MOVE for the lanes without flood work and one flood VISIT for the
+//    lanes with it, instead of 31 lanes idling through one lane's whole flood;
+//    the flood stack lives in shared memory next to the planes;
+//  * candidate links are handled direction-major (place_peg).
+// Shared memory per env: planes 0..7 (pegs, links, border flags) + the flood
+// stack.  The "blocked neighbour" plane is write-only for the rules, so it
+// stays in HBM and is OR-ed in place on the rare blocked link.
 //
 // Reference loop reproduced: upstream example.cc / RandomRolloutEvaluator
 // (LegalActions -> uniform pick -> ApplyAction until IsTerminal), with the
@@ -27,9 +38,40 @@ namespace twixt {
 
 namespace {
 
-constexpr int kPlayoutThreads = 128;  // 4 warps; n=24: 110 KB of records per block, 2 blocks per SM
-constexpr int kFloodStack = 48;
+constexpr int kPlayoutThreads = 128;  // 4 warps; n=24: 108 KB per block, 2 blocks per SM
+constexpr int kSmemPlanes = 8;        // P_RED .. P_END
+constexpr int kStackWords = 24;       // flood stack entries (one per word)
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords; }
+
+// The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
+template <int NT>
+struct PlayoutRef {
+  uint32_t* p;     // smem, this lane's column
+  uint32_t* gblk;  // global: the record's P_BLOCKED words
+  int n_rt;
+  __device__ __forceinline__ int n() const { return NT > 0 ? NT : n_rt; }
+  __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
+  __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
+  __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
+    return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
+  }
+  // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
+  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
+};
+
+struct SmemStack {
+  uint32_t* base;  // smem, this lane's column of the stack words
+  int sp;
+  bool overflow;
+  __device__ __forceinline__ bool empty() const { return sp == 0; }
+  __device__ __forceinline__ void push(uint32_t c) {
+    if (sp < kStackWords) base[(sp++) * 32] = c;
+    else overflow = true;
+  }
+  __device__ __forceinline__ uint32_t pop() { return base[(--sp) * 32]; }
+};
 
 template <int NT>
 __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutArgs a) {
@@ -40,61 +82,89 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
   const bool active = idx < a.count;
-  uint32_t* mine = smem + warp * (rw * 32) + lane;
+  uint32_t* mine = smem + warp * (playout_words(n) * 32) + lane;
   uint32_t* grec = a.records + idx * rw;
+  const int plane_quads = (kSmemPlanes * n) / 4;  // 8n words = 2n 16-byte pieces
 
+  Header h;
+  h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
   if (active) {
     const uint4* src = reinterpret_cast<const uint4*>(grec);
-    for (int q = 0; q < rw / 4; ++q) {
-      const uint4 v = src[q];
+    const uint4 hw = src[0];
+    unpack_header(hw.x, hw.y, hw.z, hw.w, h);
+    for (int q = 0; q < plane_quads; ++q) {
+      const uint4 v = src[1 + q];
       mine[(4 * q + 0) * 32] = v.x;
       mine[(4 * q + 1) * 32] = v.y;
       mine[(4 * q + 2) * 32] = v.z;
       mine[(4 * q + 3) * 32] = v.w;
     }
   }
-  // every thread only ever touches its own column of the staging buffer
+  // every thread only ever touches its own column of the staging buffer: no barrier needed
 
-  RecordRef<32, NT> b{mine, n};
-  Header h;
-  h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
-  if (active) load_header(b, h);
+  PlayoutRef<NT> b{mine, grec + kHeaderWords + P_BLOCKED * n, n};
+  SmemStack stk{mine + kSmemPlanes * n * 32, 0, false};
   const uint32_t swapped_before = h.swapped;
   const bool open_at_start = active && h.result == kOpen;
 
-  const uint64_t stream = !active ? 0ull : (a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx));
+  const uint64_t stream =
+      !active ? 0ull : (a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx));
   const uint32_t s_lo = static_cast<uint32_t>(stream), s_hi = static_cast<uint32_t>(stream >> 32);
   const uint32_t k_lo = static_cast<uint32_t>(a.seed), k_hi = static_cast<uint32_t>(a.seed >> 32);
 
   uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
   int step = 0;
-  while (h.result == kOpen && step < a.max_plies) {
-    if ((step & 3) == 0) {
-      uint32_t r[4];
-      philox4x32_10(s_lo, s_hi, static_cast<uint32_t>(step) >> 2, 0u, k_lo, k_hi, r);
-      r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3];
+  uint32_t pend = 0, origin = 0;
+  int fplane = P_START;
+  bool playing = open_at_start && a.max_plies > 0;
+  while (__any_sync(kFullMask, playing || pend != 0u || !stk.empty())) {
+    // ---- MOVE: lanes with no flood work left make their next move -----------
+    if (playing && pend == 0u && stk.empty()) {
+      if ((step & 3) == 0) {
+        uint32_t r[4];
+        philox4x32_10(s_lo, s_hi, static_cast<uint32_t>(step) >> 2, 0u, k_lo, k_hi, r);
+        r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3];
+      }
+      const uint32_t word = (step & 2) ? ((step & 1) ? r3 : r2) : ((step & 1) ? r1 : r0);
+      const int L = legal_count(h, n);
+      const int k = static_cast<int>(playout_index(word, static_cast<uint32_t>(L)));
+      int x, y;
+      select_legal(b, h, k, x, y);
+      if (a.out_actions != nullptr && step < a.trace_plies)
+        a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(x * n + y);
+      apply_begin(b, h, x, y, pend);
+      origin = static_cast<uint32_t>((x << 8) | y);
+      ++step;
+      playing = h.result == kOpen && step < a.max_plies;
     }
-    const uint32_t word = (step & 2) ? ((step & 1) ? r3 : r2) : ((step & 1) ? r1 : r0);
-    const int L = legal_count(h, n);
-    const int k = static_cast<int>(playout_index(word, static_cast<uint32_t>(L)));
-    int x, y;
-    select_legal(b, h, k, x, y);
-    if (a.out_actions != nullptr && step < a.trace_plies)
-      a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(x * n + y);
-    apply_legal_cell<kFloodStack>(b, h, x, y);
-    ++step;
+    // ---- FLOOD: one visit for the lanes that owe border-flag propagation -----
+    if (stk.empty() && pend != 0u) {
+      const bool start = (pend & kFloodStart) != 0u;
+      fplane = start ? P_START : P_END;
+      pend &= start ? ~kFloodStart : ~kFloodEnd;
+      stk.push(origin);
+    }
+    if (!stk.empty()) {
+      flood_visit(b, fplane, stk);
+      if (stk.empty() && stk.overflow) {
+        flood_closure(b, ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE, fplane);
+        stk.overflow = false;
+      }
+    }
   }
 
   if (active) {
-    store_header(b, h);
     uint4* dst = reinterpret_cast<uint4*>(grec);
-    for (int q = 0; q < rw / 4; ++q) {
+    uint4 hw;
+    pack_header(h, hw.x, hw.y, hw.z, hw.w);
+    dst[0] = hw;
+    for (int q = 0; q < plane_quads; ++q) {
       uint4 v;
       v.x = mine[(4 * q + 0) * 32];
       v.y = mine[(4 * q + 1) * 32];
       v.z = mine[(4 * q + 2) * 32];
       v.w = mine[(4 * q + 3) * 32];
-      dst[q] = v;
+      dst[1 + q] = v;
     }
     if (a.out_returns != nullptr) {
       const float r = h.result == kRedWin ? 1.0f : (h.result == kBlueWin ? -1.0f : 0.0f);
@@ -129,8 +199,7 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
 
 template <int NT>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
-  const int rw = record_words(a.n);
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * rw * sizeof(uint32_t);
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(a.n) * sizeof(uint32_t);
   const int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
   playout_kernel<NT><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
   return cudaGetLastError();
@@ -138,7 +207,7 @@ cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
 
 template <int NT>
 cudaError_t setup_nt(int n_for_size) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * record_words(n_for_size) * sizeof(uint32_t);
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
   return cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 }
 
