@@ -18,6 +18,18 @@
 using namespace twixt;
 using Rec = RecordRef<1>;
 
+// Test-only accessor with the per-column count cache the fused playout kernel keeps in shared memory.
+struct CachedRec : public RecordRef<1> {
+  uint32_t cache[6];
+  static constexpr bool kCountCache = true;
+  uint32_t cache_ld(int i) const { return cache[i]; }
+  void cache_st(int i, uint32_t v) { cache[i] = v; }
+  void note_peg(int x, int y, int delta) {
+    const uint32_t inc = (1u | ((y == 0 || y == n() - 1) ? 32u : 0u)) << (8 * (x & 3));
+    cache[x >> 2] = delta > 0 ? cache[x >> 2] + inc : cache[x >> 2] - inc;
+  }
+};
+
 extern "C" {
 
 int he_record_words(int n) { return record_words(n); }
@@ -99,6 +111,54 @@ int he_playout(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int max_pli
     if (actions_out) actions_out[step] = x * n + y;
     apply_legal_cell<TW_TEST_STACK>(b, h, x, y);
     ++step;
+  }
+  store_header(b, h);
+  return step;
+}
+
+// The same playout with the count cache and the move / flood-visit interleaving of the CUDA kernel.
+int he_playout_cached(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int max_plies, int64_t* actions_out) {
+  CachedRec b;
+  b.p = rec;
+  b.n_rt = n;
+  Header h;
+  load_header(b, h);
+  count_cache_build(b);
+  int step = 0;
+  uint32_t r[4] = {0, 0, 0, 0};
+  uint32_t pend = 0, origin = 0;
+  int fplane = P_START;
+  LocalStack<TW_TEST_STACK> stk;
+  bool playing = h.result == kOpen && max_plies > 0;
+  while (playing || pend != 0u || !stk.empty()) {
+    if (playing && pend == 0u && stk.empty()) {
+      if ((step & 3) == 0)
+        philox4x32_10(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
+                      static_cast<uint32_t>(step) >> 2, 0u, static_cast<uint32_t>(seed),
+                      static_cast<uint32_t>(seed >> 32), r);
+      int L = legal_count(h, n);
+      int k = static_cast<int>(playout_index(r[step & 3], static_cast<uint32_t>(L)));
+      int x, y;
+      select_legal(b, h, k, x, y);
+      if (actions_out) actions_out[step] = x * n + y;
+      apply_begin(b, h, x, y, pend);
+      origin = static_cast<uint32_t>((x << 8) | y);
+      ++step;
+      playing = h.result == kOpen && step < max_plies;
+    }
+    if (stk.empty() && pend != 0u) {
+      const bool start = (pend & kFloodStart) != 0u;
+      fplane = start ? P_START : P_END;
+      pend &= start ? ~kFloodStart : ~kFloodEnd;
+      stk.push(origin);
+    }
+    if (!stk.empty()) {
+      flood_visit(b, fplane, stk);
+      if (stk.empty() && stk.overflow) {
+        flood_closure(b, ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE, fplane);
+        stk.overflow = false;
+      }
+    }
   }
   store_header(b, h);
   return step;

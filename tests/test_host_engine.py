@@ -36,6 +36,7 @@ def _build(stack):
     he.he_current_player.argtypes = [C.c_void_p, C.c_int]
     he.he_observation.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     he.he_playout.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    he.he_playout_cached.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     he.he_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     he.he_select_bit.argtypes = [C.c_uint32, C.c_int]
     return he
@@ -105,14 +106,21 @@ def test_rules_match_oracle(he, oracle_mod, n):
             assert he.he_apply(P(rec), n, a) == 0
             st.apply_action(a)
             ply += 1
-    for s in range(8):  # the fused-playout policy: same Philox stream, same k-th legal pick
-        rec = np.zeros(R, dtype=np.uint32)
-        he.he_init(P(rec), n)
-        acts = np.zeros(n * n, dtype=np.int64)
-        L = he.he_playout(P(rec), n, 0x7477697854, s + (n << 33), 1 << 30, P(acts))
-        st = og.new_initial_state()
-        assert acts[:L].tolist() == st.playout_philox(0x7477697854, s + (n << 33)), (n, s)
-        assert np.array_equal(rec, st.export_record())
+    # the fused-playout policy: same Philox stream, same k-th legal pick -- with the plain column scan
+    # and with the kernel's structure (per-column count cache, moves interleaved with flood visits)
+    for fn in (he.he_playout, he.he_playout_cached):
+        for s in range(12):
+            rec = np.zeros(R, dtype=np.uint32)
+            he.he_init(P(rec), n)
+            st = og.new_initial_state()
+            if s % 3 == 2:  # from a mid-game position
+                pre = st.playout_philox(7, s, 2 + s)
+                for a in pre:
+                    assert he.he_apply(P(rec), n, a) == 0
+            acts = np.zeros(n * n, dtype=np.int64)
+            L = fn(P(rec), n, 0x7477697854, s + (n << 33), 1 << 30, P(acts))
+            assert acts[:L].tolist() == st.playout_philox(0x7477697854, s + (n << 33)), (n, s)
+            assert np.array_equal(rec, st.export_record())
 
 
 def test_rules_match_reference_generated_fixture(he):

@@ -102,6 +102,9 @@ struct RecordRef {
   }
   // the blocked plane is write-only for the rules (only ObservationTensor reads it)
   TW_HD void or_blocked(int col, uint32_t bits) { st(P_BLOCKED, col, ld(P_BLOCKED, col) | bits); }
+  // no per-column count cache on a plain record (see count_cache_* below)
+  static constexpr bool kCountCache = false;
+  TW_HD void note_peg(int, int, int) {}
 };
 
 // Flood-fill work stack kept in a thread-local array (apply kernel, host tests).
@@ -186,11 +189,19 @@ TW_HD bool is_legal(const B& b, const Header& h, int action) {
   return (legal_word(b, h, x) >> y) & 1u;
 }
 
-// Is the link (wx,wy) -> east direction de crossed by any existing link, of
-// either colour (twixtboard.cc:519-527 tests HasLink only)?
-template <class B>
-TW_HD bool crossing_blocked(const B& b, int wx, int wy, int de) {
-#define TW_X(plane, ox, mask) (b.ld_guard(P_LINK0 + (plane), wx + (ox)) & ((static_cast<uint32_t>(mask) << wy) >> 3))
+// The link words a move can touch: the four link planes over the columns
+// x-3 .. x+1 around the new peg at column x (index c = column - x + 3).  They
+// are fetched once, with independent loads, before the eight directions are
+// examined, so the crossing tests themselves run out of registers.
+struct LinkWindow {
+  uint32_t w[4][5];
+};
+
+// Is the link with west endpoint (x + ow, wy) and east direction de crossed by
+// any existing link, of either colour (twixtboard.cc:519-527 tests HasLink
+// only)?  ow in {0,-1,-2}.
+TW_HD bool crossing_blocked(const LinkWindow& lw, int ow, int wy, int de) {
+#define TW_X(plane, ox, mask) (lw.w[plane][ow + (ox) + 3] & ((static_cast<uint32_t>(mask) << wy) >> 3))
 #define TW_CROSS_CASE(d, expr) \
   case d:                      \
     return (expr) != 0u;
@@ -299,6 +310,7 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
   const int own = player == kRed ? P_RED : P_BLUE;
   const uint32_t bit = 1u << y;
   b.st(own, x, b.ld(own, x) | bit);
+  b.note_peg(x, y, +1);
   h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
   h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
 
@@ -316,25 +328,42 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
                         ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) |
                         (((w1 >> (y + 2)) & 1u) << 7);
   if (cand) {
+    // everything the eight directions may read, fetched with independent loads
+    LinkWindow lw;
+    uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 5; ++c) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int pl = 0; pl < 4; ++pl) lw.w[pl][c] = b.ld_guard(P_LINK0 + pl, x - 3 + c);
+      fs[c] = b.ld_guard(P_START, x - 2 + c);
+      fe[c] = b.ld_guard(P_END, x - 2 + c);
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int d = 0; d < 8; ++d) {
       if ((cand >> d) & 1u) {
-        const int tx = x + dir_dx(d), ty = y + dir_dy(d);
-        // the link named by its west endpoint and east direction
-        const int wx = d < 4 ? x : tx, wy = d < 4 ? y : ty, de = d & 3;
-        if (crossing_blocked(b, wx, wy, de)) {
+        const int dx = dir_dx(d), dy = dir_dy(d);
+        const int ty = y + dy;
+        // the link named by its west endpoint (x+ow, wy) and east direction de
+        const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
+        if (crossing_blocked(lw, ow, wy, de)) {
           // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the
           // bit pointing east is ever read (twixtcell.h:82-84) and it always
           // lands on the west endpoint
-          b.or_blocked(wx, 1u << wy);
+          b.or_blocked(x + ow, 1u << wy);
         } else {
-          b.st(P_LINK0 + de, wx, b.ld(P_LINK0 + de, wx) | (1u << wy));
+          // each direction owns a distinct (plane, column) word, and links made
+          // earlier in this move never cross later ones (they share the new peg)
+          b.st(P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
           new_links = true;
-          if ((b.ld(P_START, tx) >> ty) & 1u) to_start = true;   // twixtboard.cc:538-540
-          else if ((b.ld(P_END, tx) >> ty) & 1u) to_end = true;  // 541-543
-          else neutral = true;                                   // 544-546
+          if ((fs[dx + 2] >> ty) & 1u) to_start = true;        // twixtboard.cc:538-540
+          else if ((fe[dx + 2] >> ty) & 1u) to_end = true;     // 541-543
+          else neutral = true;                                 // 544-546
         }
       }
     }
@@ -360,6 +389,7 @@ TW_HD void apply_begin(B& b, Header& h, int& x, int& y, uint32_t& pending) {
     // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
     // on the cell turned by 90 degrees (471-473)
     b.st(P_RED, x, b.ld(P_RED, x) & ~(1u << y));
+    b.note_peg(x, y, -1);
     b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
     b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
     h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
@@ -404,20 +434,109 @@ TW_HD int select_bit(uint32_t w, int k) {
   return pos;
 }
 
+// ---- per-column count cache (fused playout only) ---------------------------
+// Scanning 24 column words per move to find the k-th legal cell is the largest
+// fixed cost of a playout step.  An accessor with kCountCache keeps, next to the
+// planes, one byte per column: bits 0-4 = pegs in the column, bits 5-6 = pegs of
+// the column on the two border rows (0 and n-1).  From these the mover's legal
+// count of every column follows without touching the planes
+//   red : n - pegs              (columns 1..n-2; twixtboard.cc:266-273)
+//   blue: (n-2) - pegs + border (rows 1..n-2 of every column)
+//   ply 1: n-2 for every column (blue's list is still the initial one)
+// and four columns are handled per 32-bit word (bytewise arithmetic, byte prefix
+// sums by one multiply).  The accessor provides cache_ld(i) / cache_st(i, v).
+TW_HD uint32_t bytes4(uint32_t v) { return v * 0x01010101u; }
+
+// 0xFF in byte j of word i iff column 4i+j is in [lo, hi]
+TW_HD uint32_t column_byte_mask(int i, int lo, int hi) {
+  uint32_t m = 0;
+  for (int j = 0; j < 4; ++j) {
+    const int x = 4 * i + j;
+    if (x >= lo && x <= hi) m |= 0xFFu << (8 * j);
+  }
+  return m;
+}
+
+// per-byte (a > b), 0xFF / 0x00, all bytes < 0x80
+TW_HD uint32_t bytes_gt(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __vcmpgtu4(a, b);
+#else
+  uint32_t r = 0;
+  for (int j = 0; j < 4; ++j)
+    if (((a >> (8 * j)) & 0xFFu) > ((b >> (8 * j)) & 0xFFu)) r |= 0xFFu << (8 * j);
+  return r;
+#endif
+}
+
+template <class B>
+TW_HD void count_cache_build(B& b) {
+  const int n = b.n();
+  const uint32_t border = 1u | (1u << (n - 1));
+  for (int i = 0; i < (n + 3) / 4; ++i) {
+    uint32_t w = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int x = 4 * i + j;
+      if (x < n) {
+        const uint32_t occ = b.ld(P_RED, x) | b.ld(P_BLUE, x);
+        w |= static_cast<uint32_t>(tw_popc(occ) | (tw_popc(occ & border) << 5)) << (8 * j);
+      }
+    }
+    b.cache_st(i, w);
+  }
+}
+
+// legal cells per column of the player to move, four columns per word
+template <class B>
+TW_HD uint32_t count_cache_legal4(const B& b, const Header& h, int i) {
+  const int n = b.n();
+  if (h.ply == 1u) return bytes4(static_cast<uint32_t>(n - 2)) & column_byte_mask(i, 0, n - 1);
+  const uint32_t w = b.cache_ld(i);
+  const uint32_t pegs = w & 0x1F1F1F1Fu, brd = (w >> 5) & 0x03030303u;
+  if ((h.ply & 1u) == kRed) return (bytes4(static_cast<uint32_t>(n)) - pegs) & column_byte_mask(i, 1, n - 2);
+  return (bytes4(static_cast<uint32_t>(n - 2)) - pegs + brd) & column_byte_mask(i, 0, n - 1);
+}
+
+template <class B>
+TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, int& out_y) {
+  const int n = b.n();
+  uint32_t sp = 0;  // byte prefix sums of the selected word
+  int si = 0, sk = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < (n + 3) / 4; ++i) {
+    const uint32_t p4 = count_cache_legal4(b, h, i) * 0x01010101u;  // inclusive byte prefix sums
+    if (k >= 0) { sp = p4; si = i; sk = k; }
+    k -= static_cast<int>(p4 >> 24);
+  }
+  // first byte whose inclusive prefix exceeds sk
+  const uint32_t gt = bytes_gt(sp, bytes4(static_cast<uint32_t>(sk)));
+  const int j = tw_ctz(gt) >> 3;
+  const int before = j == 0 ? 0 : static_cast<int>((sp >> (8 * (j - 1))) & 0xFFu);
+  const int x = 4 * si + j;
+  out_x = x;
+  out_y = select_bit(legal_word(b, h, x), sk - before);
+}
+
 // The k-th action (0-based) of the ascending legal list, as a cell; k <
 // legal_count.  Ascending action order is column-major (action = x*n+y,
 // twixtboard.cc:603-605), i.e. the order of the column words.
 template <class B>
 TW_HD void select_legal(const B& b, const Header& h, int k, int& out_x, int& out_y) {
-  int sx = 0, sk = 0;
-  uint32_t sw = 0;
-  for (int x = 0; x < b.n(); ++x) {
-    uint32_t w = legal_word(b, h, x);
-    if (k >= 0) { sx = x; sw = w; sk = k; }
-    k -= tw_popc(w);
+  if constexpr (B::kCountCache) {
+    select_legal_cached(b, h, k, out_x, out_y);
+  } else {
+    int sx = 0, sk = 0;
+    uint32_t sw = 0;
+    for (int x = 0; x < b.n(); ++x) {
+      uint32_t w = legal_word(b, h, x);
+      if (k >= 0) { sx = x; sw = w; sk = k; }
+      k -= tw_popc(w);
+    }
+    out_x = sx;
+    out_y = select_bit(sw, sk);
   }
-  out_x = sx;
-  out_y = select_bit(sw, sk);
 }
 
 // Column word of "peg has at least one link" (Cell::HasLinks, twixtcell.h:78).

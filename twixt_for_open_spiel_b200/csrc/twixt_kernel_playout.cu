@@ -21,7 +21,8 @@
 //    the flood stack lives in shared memory next to the planes;
 //  * candidate links are handled direction-major (place_peg).
 // Shared memory per env: planes 0..7 (pegs, links, border flags) + the flood
-// stack.  The "blocked neighbour" plane is write-only for the rules, so it
+// stack + a per-column count cache that replaces the 24-word legal scan by 6
+// bytewise words (twixt_engine.cuh, count_cache_*).  The "blocked neighbour" plane is write-only for the rules, so it
 // stays in HBM and is OR-ed in place on the rare blocked link.
 //
 // Reference loop reproduced: upstream example.cc / RandomRolloutEvaluator
@@ -41,9 +42,10 @@ namespace {
 constexpr int kPlayoutThreads = 128;  // 4 warps; n=24: 108 KB per block, 2 blocks per SM
 constexpr int kSmemPlanes = 8;        // P_RED .. P_END
 constexpr int kStackWords = 24;       // flood stack entries (one per word)
+constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
-__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords; }
+__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
 
 // The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
 template <int NT>
@@ -59,6 +61,16 @@ struct PlayoutRef {
   }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
   __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
+  // per-column count cache (twixt_engine.cuh, count_cache_*), after the planes and the stack
+  static constexpr bool kCountCache = true;
+  __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
+  __device__ __forceinline__ uint32_t cache_ld(int i) const { return *cache_word(i); }
+  __device__ __forceinline__ void cache_st(int i, uint32_t v) { *cache_word(i) = v; }
+  __device__ __forceinline__ void note_peg(int x, int y, int delta) {
+    const uint32_t inc = (1u | ((y == 0 || y == n() - 1) ? 32u : 0u)) << (8 * (x & 3));
+    uint32_t* w = cache_word(x >> 2);
+    *w = delta > 0 ? *w + inc : *w - inc;
+  }
 };
 
 struct SmemStack {
@@ -104,6 +116,7 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
 
   PlayoutRef<NT> b{mine, grec + kHeaderWords + P_BLOCKED * n, n};
   SmemStack stk{mine + kSmemPlanes * n * 32, 0, false};
+  if (active) count_cache_build(b);
   const uint32_t swapped_before = h.swapped;
   const bool open_at_start = active && h.result == kOpen;
 
