@@ -100,6 +100,11 @@ struct RecordRef {
   TW_HD uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
+  // the two peg planes (P_RED / P_BLUE) are the hot ones: an accessor may keep them
+  // in faster memory than the rest, so the rules name them separately
+  TW_HD uint32_t ld_pegs(int plane, int col) const { return ld(plane, col); }
+  TW_HD void st_pegs(int plane, int col, uint32_t v) { st(plane, col, v); }
+  TW_HD uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // the blocked plane is write-only for the rules (only ObservationTensor reads it)
   TW_HD void or_blocked(int col, uint32_t bits) { st(P_BLOCKED, col, ld(P_BLOCKED, col) | bits); }
   // no per-column count cache on a plain record (see count_cache_* below)
@@ -177,7 +182,7 @@ TW_HD uint32_t legal_word(const B& b, const Header& h, int x) {
   int player = static_cast<int>(h.ply & 1u);
   uint32_t play = playable_word(b.n(), player, x);
   if (h.ply == 1u) return play;
-  return play & ~(b.ld(P_RED, x) | b.ld(P_BLUE, x));
+  return play & ~(b.ld_pegs(P_RED, x) | b.ld_pegs(P_BLUE, x));
 }
 
 template <class B>
@@ -265,7 +270,7 @@ TW_HD_NOINLINE void flood_closure(B& b, int own_plane, int flag_plane) {
   while (changed) {
     changed = false;
     for (int cx = 0; cx < b.n(); ++cx) {
-      uint32_t w = b.ld(flag_plane, cx) & b.ld(own_plane, cx);
+      uint32_t w = b.ld(flag_plane, cx) & b.ld_pegs(own_plane, cx);
       while (w) {
         const int cy = tw_ctz(w);
         w &= w - 1u;
@@ -309,7 +314,7 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
   const int n = b.n();
   const int own = player == kRed ? P_RED : P_BLUE;
   const uint32_t bit = 1u << y;
-  b.st(own, x, b.ld(own, x) | bit);
+  b.st_pegs(own, x, b.ld_pegs(own, x) | bit);
   b.note_peg(x, y, +1);
   h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
   h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
@@ -321,8 +326,8 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
   bool neutral = false, new_links = false;
 
   // own-colour pegs a knight's move away, as a Compass-ordered 8-bit mask
-  const uint32_t e1 = b.ld_guard(own, x + 1), e2 = b.ld_guard(own, x + 2);
-  const uint32_t w1 = b.ld_guard(own, x - 1), w2 = b.ld_guard(own, x - 2);
+  const uint32_t e1 = b.ld_pegs_guard(own, x + 1), e2 = b.ld_pegs_guard(own, x + 2);
+  const uint32_t w1 = b.ld_pegs_guard(own, x - 1), w2 = b.ld_pegs_guard(own, x - 2);
   const uint32_t cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
                         ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) |
                         ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) |
@@ -346,26 +351,29 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
 #pragma unroll
 #endif
     for (int d = 0; d < 8; ++d) {
-      if ((cand >> d) & 1u) {
-        const int dx = dir_dx(d), dy = dir_dy(d);
-        const int ty = y + dy;
-        // the link named by its west endpoint (x+ow, wy) and east direction de
-        const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
-        if (crossing_blocked(lw, ow, wy, de)) {
-          // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the
-          // bit pointing east is ever read (twixtcell.h:82-84) and it always
-          // lands on the west endpoint
-          b.or_blocked(x + ow, 1u << wy);
-        } else {
-          // each direction owns a distinct (plane, column) word, and links made
-          // earlier in this move never cross later ones (they share the new peg)
-          b.st(P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
-          new_links = true;
-          if ((fs[dx + 2] >> ty) & 1u) to_start = true;        // twixtboard.cc:538-540
-          else if ((fe[dx + 2] >> ty) & 1u) to_end = true;     // 541-543
-          else neutral = true;                                 // 544-546
-        }
+      // straight-line per direction (no branch around the test: it is a dozen
+      // register-only instructions, cheaper than a divergent branch)
+      const int dx = dir_dx(d), dy = dir_dy(d);
+      const bool is_cand = (cand >> d) & 1u;
+      const int ty = is_cand ? y + dy : 0;  // keeps every shift count in range for non-candidates
+      // the link named by its west endpoint (x+ow, wy) and east direction de
+      const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
+      const bool blocked = crossing_blocked(lw, ow, wy, de);
+      if (is_cand && blocked) {
+        // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
+        // pointing east is ever read (twixtcell.h:82-84) and it always lands on
+        // the west endpoint
+        b.or_blocked(x + ow, 1u << wy);
       }
+      const bool make = is_cand && !blocked;
+      // each direction owns a distinct (plane, column) word, and links made
+      // earlier in this move never cross later ones (they share the new peg)
+      if (make) b.st(P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
+      const bool ts = (fs[dx + 2] >> ty) & 1u, te = (fe[dx + 2] >> ty) & 1u;
+      new_links |= make;
+      to_start |= make && ts;                // twixtboard.cc:538-540
+      to_end |= make && !ts && te;           // 541-543
+      neutral |= make && !ts && !te;         // 544-546
     }
   }
   if (to_start) b.st(P_START, x, b.ld(P_START, x) | bit);
@@ -388,7 +396,7 @@ TW_HD void apply_begin(B& b, Header& h, int& x, int& y, uint32_t& pending) {
   if (h.ply == 1u && action == h.move_one) {
     // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
     // on the cell turned by 90 degrees (471-473)
-    b.st(P_RED, x, b.ld(P_RED, x) & ~(1u << y));
+    b.st_pegs(P_RED, x, b.ld_pegs(P_RED, x) & ~(1u << y));
     b.note_peg(x, y, -1);
     b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
     b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
@@ -478,7 +486,7 @@ TW_HD void count_cache_build(B& b) {
     for (int j = 0; j < 4; ++j) {
       const int x = 4 * i + j;
       if (x < n) {
-        const uint32_t occ = b.ld(P_RED, x) | b.ld(P_BLUE, x);
+        const uint32_t occ = b.ld_pegs(P_RED, x) | b.ld_pegs(P_BLUE, x);
         w |= static_cast<uint32_t>(tw_popc(occ) | (tw_popc(occ & border) << 5)) << (8 * j);
       }
     }
@@ -557,7 +565,7 @@ template <class B>
 TW_HD uint32_t obs_plane_word(const B& b, int plane, int x) {
   const int own = plane < 6 ? P_RED : P_BLUE;
   const int k = plane < 6 ? plane : plane - 6;
-  const uint32_t pegs = b.ld(own, x);
+  const uint32_t pegs = b.ld_pegs(own, x);
   if (k == 0) return pegs & ~haslink_word(b, x);
   if (k == 5) return pegs & b.ld(P_BLOCKED, x);
   return pegs & b.ld(P_LINK0 + (k - 1), x);

@@ -30,6 +30,7 @@
 // per-move semantics of twixtboard.cc:457-499.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "twixt_engine.cuh"
 #include "twixt_kernels.cuh"
@@ -39,31 +40,54 @@ namespace twixt {
 
 namespace {
 
-constexpr int kPlayoutThreads = 128;  // 4 warps; n=24: 108 KB per block, 2 blocks per SM
-constexpr int kSmemPlanes = 8;        // P_RED .. P_END
-constexpr int kStackWords = 24;       // flood stack entries (one per word)
+constexpr int kPlayoutThreads = 128;  // 4 warps per block
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
-__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
+// Two placements of the env state during a playout (template parameter SP =
+// number of leading planes staged in shared memory):
+//   SP = 8  all planes the rules read (pegs, links, border flags) on chip;
+//           888 B per env at n=24 -> 256 envs = 8 warps per SM
+//   SP = 2  only the two peg planes (touched by every move) on chip, links and
+//           border flags are read/written in place in HBM/L2 (a move fetches its
+//           whole 5-column link window with independent loads, one round trip);
+//           264 B per env at n=24 -> 768 envs = 24 warps per SM to hide latency
+template <int SP>
+struct PlayoutCfg {
+  static constexpr int kStackWords = SP >= 8 ? 24 : 12;  // flood stack entries (one per word)
+  __host__ __device__ static constexpr int words(int n) { return SP * n + kStackWords + kCacheWords; }
+};
 
-// The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
-template <int NT>
+// The env's planes: the first SP in shared memory (stride 32 words), the rest in its HBM record.
+template <int NT, int SP>
 struct PlayoutRef {
   uint32_t* p;     // smem, this lane's column
-  uint32_t* gblk;  // global: the record's P_BLOCKED words
+  uint32_t* gpl;   // global: the record's plane words (record + kHeaderWords)
   int n_rt;
   __device__ __forceinline__ int n() const { return NT > 0 ? NT : n_rt; }
-  __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
-  __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
+  __device__ __forceinline__ uint32_t ld(int plane, int col) const {
+    return plane < SP ? p[(plane * n() + col) * 32] : gpl[plane * n() + col];
+  }
+  __device__ __forceinline__ void st(int plane, int col, uint32_t v) {
+    if (plane < SP) p[(plane * n() + col) * 32] = v;
+    else gpl[plane * n() + col] = v;
+  }
   __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
+  // peg planes are always on chip
+  __device__ __forceinline__ uint32_t ld_pegs(int plane, int col) const { return p[(plane * n() + col) * 32]; }
+  __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
+  __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const {
+    return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld_pegs(plane, col) : 0u;
+  }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
-  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
+  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gpl + P_BLOCKED * n() + col, bits); }
   // per-column count cache (twixt_engine.cuh, count_cache_*), after the planes and the stack
   static constexpr bool kCountCache = true;
-  __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
+  __device__ __forceinline__ uint32_t* cache_word(int i) const {
+    return p + (SP * n() + PlayoutCfg<SP>::kStackWords + i) * 32;
+  }
   __device__ __forceinline__ uint32_t cache_ld(int i) const { return *cache_word(i); }
   __device__ __forceinline__ void cache_st(int i, uint32_t v) { *cache_word(i) = v; }
   __device__ __forceinline__ void note_peg(int x, int y, int delta) {
@@ -73,19 +97,20 @@ struct PlayoutRef {
   }
 };
 
+template <int CAP>
 struct SmemStack {
   uint32_t* base;  // smem, this lane's column of the stack words
   int sp;
   bool overflow;
   __device__ __forceinline__ bool empty() const { return sp == 0; }
   __device__ __forceinline__ void push(uint32_t c) {
-    if (sp < kStackWords) base[(sp++) * 32] = c;
+    if (sp < CAP) base[(sp++) * 32] = c;
     else overflow = true;
   }
   __device__ __forceinline__ uint32_t pop() { return base[(--sp) * 32]; }
 };
 
-template <int NT>
+template <int NT, int SP>
 __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutArgs a) {
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
@@ -94,28 +119,26 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
   const bool active = idx < a.count;
-  uint32_t* mine = smem + warp * (playout_words(n) * 32) + lane;
+  uint32_t* mine = smem + warp * (PlayoutCfg<SP>::words(n) * 32) + lane;
   uint32_t* grec = a.records + idx * rw;
-  const int plane_quads = (kSmemPlanes * n) / 4;  // 8n words = 2n 16-byte pieces
+  const int staged_pairs = (SP * n) / 2;  // staged plane words, as 8-byte pieces (planes start 16-byte aligned)
 
   Header h;
   h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
   if (active) {
-    const uint4* src = reinterpret_cast<const uint4*>(grec);
-    const uint4 hw = src[0];
+    const uint4 hw = *reinterpret_cast<const uint4*>(grec);
     unpack_header(hw.x, hw.y, hw.z, hw.w, h);
-    for (int q = 0; q < plane_quads; ++q) {
-      const uint4 v = src[1 + q];
-      mine[(4 * q + 0) * 32] = v.x;
-      mine[(4 * q + 1) * 32] = v.y;
-      mine[(4 * q + 2) * 32] = v.z;
-      mine[(4 * q + 3) * 32] = v.w;
+    const uint2* src = reinterpret_cast<const uint2*>(grec + kHeaderWords);
+    for (int q = 0; q < staged_pairs; ++q) {
+      const uint2 v = src[q];
+      mine[(2 * q + 0) * 32] = v.x;
+      mine[(2 * q + 1) * 32] = v.y;
     }
   }
   // every thread only ever touches its own column of the staging buffer: no barrier needed
 
-  PlayoutRef<NT> b{mine, grec + kHeaderWords + P_BLOCKED * n, n};
-  SmemStack stk{mine + kSmemPlanes * n * 32, 0, false};
+  PlayoutRef<NT, SP> b{mine, grec + kHeaderWords, n};
+  SmemStack<PlayoutCfg<SP>::kStackWords> stk{mine + SP * n * 32, 0, false};
   if (active) count_cache_build(b);
   const uint32_t swapped_before = h.swapped;
   const bool open_at_start = active && h.result == kOpen;
@@ -167,18 +190,11 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   }
 
   if (active) {
-    uint4* dst = reinterpret_cast<uint4*>(grec);
     uint4 hw;
     pack_header(h, hw.x, hw.y, hw.z, hw.w);
-    dst[0] = hw;
-    for (int q = 0; q < plane_quads; ++q) {
-      uint4 v;
-      v.x = mine[(4 * q + 0) * 32];
-      v.y = mine[(4 * q + 1) * 32];
-      v.z = mine[(4 * q + 2) * 32];
-      v.w = mine[(4 * q + 3) * 32];
-      dst[1 + q] = v;
-    }
+    *reinterpret_cast<uint4*>(grec) = hw;
+    uint2* dst = reinterpret_cast<uint2*>(grec + kHeaderWords);
+    for (int q = 0; q < staged_pairs; ++q) dst[q] = make_uint2(mine[(2 * q + 0) * 32], mine[(2 * q + 1) * 32]);
     if (a.out_returns != nullptr) {
       const float r = h.result == kRedWin ? 1.0f : (h.result == kBlueWin ? -1.0f : 0.0f);
       reinterpret_cast<float2*>(a.out_returns)[idx] = make_float2(r, r == 0.0f ? 0.0f : -r);
@@ -210,39 +226,58 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   }
 }
 
-template <int NT>
+int g_smem_planes = 8;  // TWIXT_PLAYOUT_SMEM_PLANES=2|8 (experiments); see PlayoutCfg
+
+template <int NT, int SP>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(a.n) * sizeof(uint32_t);
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * PlayoutCfg<SP>::words(a.n) * sizeof(uint32_t);
   const int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
-  playout_kernel<NT><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
+  playout_kernel<NT, SP><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
-template <int NT>
+template <int NT, int SP>
 cudaError_t setup_nt(int n_for_size) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
-  return cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * PlayoutCfg<SP>::words(n_for_size) * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(playout_kernel<NT, SP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
+
+template <int SP>
+cudaError_t launch_sp(const PlayoutArgs& a, cudaStream_t s) {
+  switch (a.n) {
+    case 8: return launch_nt<8, SP>(a, s);
+    case 12: return launch_nt<12, SP>(a, s);
+    case 24: return launch_nt<24, SP>(a, s);
+    default: return launch_nt<0, SP>(a, s);
+  }
+}
+
+template <int SP>
+cudaError_t setup_sp() {
+  cudaError_t e;
+  if ((e = setup_nt<0, SP>(24)) != cudaSuccess) return e;
+  if ((e = setup_nt<8, SP>(8)) != cudaSuccess) return e;
+  if ((e = setup_nt<12, SP>(12)) != cudaSuccess) return e;
+  return setup_nt<24, SP>(24);
 }
 
 }  // namespace
 
 cudaError_t playout_setup() {
-  cudaError_t e;
-  if ((e = setup_nt<0>(24)) != cudaSuccess) return e;
-  if ((e = setup_nt<8>(8)) != cudaSuccess) return e;
-  if ((e = setup_nt<12>(12)) != cudaSuccess) return e;
-  if ((e = setup_nt<24>(24)) != cudaSuccess) return e;
-  return cudaSuccess;
+  const char* v = getenv("TWIXT_PLAYOUT_SMEM_PLANES");
+  if (v != nullptr && (v[0] == '2' || v[0] == '8')) g_smem_planes = v[0] - '0';
+  cudaError_t e = setup_sp<8>();
+  if (e != cudaSuccess) return e;
+  return setup_sp<2>();
 }
 
 cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s) {
   if (a.count <= 0) return cudaSuccess;
-  switch (a.n) {
-    case 8: return launch_nt<8>(a, s);
-    case 12: return launch_nt<12>(a, s);
-    case 24: return launch_nt<24>(a, s);
-    default: return launch_nt<0>(a, s);
-  }
+  return g_smem_planes == 2 ? launch_sp<2>(a, s) : launch_sp<8>(a, s);
 }
 
 }  // namespace twixt
