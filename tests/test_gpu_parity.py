@@ -65,7 +65,28 @@ def test_lockstep_random_games(oracle_mod, n):
     rng = random.Random(1000 + n)
     num = 96 if n <= 12 else 40
     games = [random_game_actions(og, rng, force_swap=(i % 3 == 0)) for i in range(num)]
-    _lockstep(oracle_mod, n, games, check_obs_every=1 if n <= 12 else 9)
+    _lockstep(oracle_mod, n, games, check_obs_every=1 if n <= 12 else 3)
+
+
+@pytest.mark.parametrize("n", list(range(5, 25)))
+def test_observation_every_size_late_game(oracle_mod, n):
+    """All 12 planes (incl. the sparse blocked-link planes 5/11) on crowded boards, every board size."""
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    og = oracle_mod.OracleGame(n)
+    E = 64
+    batch = TwixTBatch(n, E, 0, SEED)
+    budget = max(4, (n * n * 3) // 5)
+    batch.playout(max_plies=budget)
+    obs = batch.observation()
+    seen = np.zeros(12, dtype=bool)
+    for e in range(E):
+        st = og.new_initial_state()
+        st.playout_philox(SEED, e, budget)
+        want = st.observation_tensor(0)
+        assert np.array_equal(obs[e].reshape(-1), want), (n, e)
+        seen |= want.reshape(12, -1).any(axis=1)
+    assert seen.all(), seen  # every plane carried data, so every plane was really compared
+    batch.close()
 
 
 def test_lockstep_draw_seeking_n5(oracle_mod):

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/twixt_b200.h"
 #include "twixt_engine.cuh"
 #include "twixt_kernels.cuh"
 
@@ -55,62 +56,134 @@ __global__ void clone_kernel(uint32_t* __restrict__ dst, const uint32_t* __restr
 }
 
 // ------------------------------------------------------ legal list / mask ---
-// Legal word of column `lane` for the warp's env (0 for lanes >= n and for
-// terminal envs): TwixTState::LegalActions twixt.h:86-90.
-__device__ __forceinline__ uint32_t warp_legal_word(const uint32_t* rec, int n, int lane) {
-  const uint4 hw = ldg128(rec);
+// One warp per env at a time, lane = board column, persistent warps striding
+// over the env range (a grid of 1 M tiny blocks is bound by block launch rate,
+// not by HBM).  The three loads an env needs (header, red word, blue word of
+// the lane's column) are independent and are issued one env ahead.
+constexpr int kLegalWarps = 8;  // warps per block
+
+struct LegalInputs {
+  uint4 hw;
+  uint32_t red, blue;
+};
+
+__device__ __forceinline__ LegalInputs legal_fetch(const uint32_t* rec, int n, int lane) {
+  LegalInputs in;
+  in.hw = ldg128(rec);
+  const int col = lane < n ? lane : 0;
+  in.red = __ldg(rec + kHeaderWords + col);
+  in.blue = __ldg(rec + kHeaderWords + n + col);
+  return in;
+}
+
+// Legal word of column `lane` (0 for lanes >= n and for terminal envs):
+// TwixTState::LegalActions twixt.h:86-90.
+__device__ __forceinline__ uint32_t legal_word_of(const LegalInputs& in, int n, int lane) {
   Header h;
-  unpack_header(hw.x, hw.y, hw.z, hw.w, h);
+  unpack_header(in.hw.x, in.hw.y, in.hw.z, in.hw.w, h);
   if (h.result != kOpen || lane >= n) return 0u;
-  const int player = static_cast<int>(h.ply & 1u);
-  const uint32_t play = playable_word(n, player, lane);
+  const uint32_t play = playable_word(n, static_cast<int>(h.ply & 1u), lane);
   if (h.ply == 1u) return play;
-  const uint32_t occ = __ldg(rec + kHeaderWords + lane) | __ldg(rec + kHeaderWords + n + lane);
-  return play & ~occ;
+  return play & ~(in.red | in.blue);
 }
 
+// popc + warp prefix sum give every column its offset in the ascending list
+// (action = x*n + y is column-major, twixtboard.cc:603-605); each lane expands
+// its column into a shared-memory row, then the warp streams the row out with
+// coalesced (vector) stores.
 template <typename T>
-__global__ void legal_actions_kernel(const uint32_t* __restrict__ records, int64_t count, int n, int rw,
-                                     T* __restrict__ out_actions, int64_t stride, int32_t* __restrict__ out_counts) {
-  const int lane = threadIdx.x & 31;
-  const int64_t env = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
+    const uint32_t* __restrict__ records, int64_t count, int n, int rw, T* __restrict__ out_actions, int64_t stride,
+    int32_t* __restrict__ out_counts) {
+  __shared__ __align__(16) T rows[kLegalWarps][TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLegalWarps;
+  int64_t env = blockIdx.x * static_cast<int64_t>(kLegalWarps) + warp;
   if (env >= count) return;  // whole warp leaves together
-  const uint32_t w = warp_legal_word(records + env * rw, n, lane);
-  const int c = __popc(w);
-  int incl = c;
+  T* row = rows[warp];
+  LegalInputs cur = legal_fetch(records + env * rw, n, lane);
+  for (; env < count; env += nwarps) {
+    const int64_t next = env + nwarps;
+    LegalInputs nxt = cur;
+    if (next < count) nxt = legal_fetch(records + next * rw, n, lane);
+    const uint32_t w = legal_word_of(cur, n, lane);
+    const int c = __popc(w);
+    int incl = c;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFullMask, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int total = __shfl_sync(kFullMask, incl, 31);
-  if (out_counts != nullptr && lane == 0) out_counts[env] = total;
-  if (out_actions != nullptr) {
-    T* row = out_actions + env * stride + (incl - c);
-    uint32_t rest = w;
-    int r = 0;
-    while (rest) {  // ascending rows of this column: action = x*n + y
-      const int y = __ffs(static_cast<int>(rest)) - 1;
-      rest &= rest - 1u;
-      row[r++] = static_cast<T>(lane * n + y);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += t;
     }
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    if (out_counts != nullptr && lane == 0) out_counts[env] = total;
+    if (out_actions != nullptr) {
+      uint32_t rest = w;
+      int r = incl - c;
+      const int base = lane * n;
+      while (rest) {  // ascending rows of this column
+        const int y = __ffs(static_cast<int>(rest)) - 1;
+        rest &= rest - 1u;
+        row[r++] = static_cast<T>(base + y);
+      }
+      __syncwarp();
+      T* dst = out_actions + env * stride;
+      constexpr int kPerVec = 16 / static_cast<int>(sizeof(T));
+      int done = 0;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int nvec = total / kPerVec;
+        for (int v = lane; v < nvec; v += 32)
+          reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(row)[v];
+        done = nvec * kPerVec;
+      }
+      for (int i = done + lane; i < total; i += 32) dst[i] = row[i];
+      __syncwarp();  // the row is reused by the next env
+    }
+    cur = nxt;
   }
 }
 
-__global__ void legal_mask_kernel(const uint32_t* __restrict__ records, int64_t count, int n, int rw,
-                                  uint8_t* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t env = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+// [count, n*n] uint8 mask.  For n % 4 == 0 every lane turns its column word into n mask bytes with the
+// nibble-spreading multiply (4 bits -> 4 bytes), the warp stages the n*n bytes in shared memory and
+// writes them out with 16-byte stores; other sizes take the byte-wise path.
+template <bool kFast>
+__global__ void __launch_bounds__(kLegalWarps * 32) legal_mask_kernel(const uint32_t* __restrict__ records,
+                                                                      int64_t count, int n, int rw,
+                                                                      uint8_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t rows[kLegalWarps][TWIXT_MAX_BOARD_SIZE * TWIXT_MAX_BOARD_SIZE / 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLegalWarps;
+  int64_t env = blockIdx.x * static_cast<int64_t>(kLegalWarps) + warp;
   if (env >= count) return;
-  const uint32_t w = warp_legal_word(records + env * rw, n, lane);
   const int cells = n * n;
-  uint8_t* row = out + env * cells;
-  for (int base = 0; base < cells; base += 32) {
-    const int c = base + lane;
-    const int x = min(c / n, n - 1);
-    const int y = c - x * n;
-    const uint32_t col = __shfl_sync(kFullMask, w, x);
-    if (c < cells) row[c] = static_cast<uint8_t>((col >> y) & 1u);
+  uint32_t* row = rows[warp];
+  LegalInputs cur = legal_fetch(records + env * rw, n, lane);
+  for (; env < count; env += nwarps) {
+    const int64_t next = env + nwarps;
+    LegalInputs nxt = cur;
+    if (next < count) nxt = legal_fetch(records + next * rw, n, lane);
+    const uint32_t w = legal_word_of(cur, n, lane);
+    uint8_t* dst = out + env * cells;
+    if (kFast) {
+      if (lane < n) {
+        const int words = n >> 2;
+        for (int q = 0; q < words; ++q)  // bits 4q..4q+3 -> one byte each
+          row[lane * words + q] = (((w >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
+      }
+      __syncwarp();
+      const int nvec = cells >> 4;  // n % 4 == 0  =>  n*n % 16 == 0
+      for (int v = lane; v < nvec; v += 32)
+        reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(row)[v];
+      __syncwarp();
+    } else {
+      for (int base = 0; base < cells; base += 32) {
+        const int c = base + lane;
+        const int x = min(c / n, n - 1);
+        const int y = c - x * n;
+        const uint32_t col = __shfl_sync(kFullMask, w, x);
+        if (c < cells) dst[c] = static_cast<uint8_t>((col >> y) & 1u);
+      }
+    }
+    cur = nxt;
   }
 }
 
@@ -164,53 +237,69 @@ __global__ void query_kernel(const uint32_t* __restrict__ records, int64_t count
 
 // ---------------------------------------------------------- observation ---
 // TwixTState::ObservationTensor (twixt.cc:101-132): [12, n, n-2] float32 per
-// env.  The 12 planes are first formed as column words in shared memory
-// (obs_plane_word), then every thread writes 4 consecutive floats.
+// env, HBM-write bound (25 KB out per 0.9 KB in at n=24).  Persistent blocks
+// stride over the envs.  Per env: (1) the 12 planes are formed as column words
+// in BOARD coordinates (obs_plane_word), (2) re-cut into one bit-word per
+// OUTPUT row (GetTensorPosition, twixtboard.cc:590-597: red planes are a
+// transpose, blue planes a bit reversal), (3) every thread expands 4
+// consecutive output floats from those row words and stores them as a float4.
 constexpr int kObsThreads = 256;
-constexpr int kObsPlaneWords = 12 * 24;
+constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
 
 template <bool kVec4>
 __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t* __restrict__ records, int64_t count,
                                                                   int n, int rw, float* __restrict__ out) {
-  __shared__ uint32_t planes[kObsPlaneWords];  // [12][n]
-  const int64_t env = blockIdx.x;
-  if (env >= count) return;
-  RecordRef<1> b{const_cast<uint32_t*>(records + env * rw), n};
-  for (int t = threadIdx.x; t < 12 * n; t += kObsThreads) {
-    const int p = t / n;
-    planes[t] = obs_plane_word(b, p, t - p * n);
-  }
-  __syncthreads();
+  __shared__ uint32_t planes[kObsPlaneWords];  // [12][n] column words, board coordinates
+  __shared__ uint32_t rowbits[kObsPlaneWords]; // [12][n] output rows, bit c = tensor column c
   const int w = n - 2;
-  const int plane_size = n * w;
-  const int total = 12 * plane_size;
-  float* dst = out + env * static_cast<int64_t>(total);
-  // exact for the ranges used (j < 2^13, divisors < 2^10): see DESIGN.md
-  const uint32_t m_plane = ((1u << 24) + plane_size - 1) / plane_size;
-  const uint32_t m_row = ((1u << 24) + w - 1) / w;
-  constexpr int kPer = kVec4 ? 4 : 1;
-  for (int j = threadIdx.x * kPer; j < total; j += kObsThreads * kPer) {
-    int p = static_cast<int>((static_cast<uint32_t>(j) * m_plane) >> 24);
-    const int rem = j - p * plane_size;
-    int r = static_cast<int>((static_cast<uint32_t>(rem) * m_row) >> 24);
-    int c = rem - r * w;
-    float v[kPer];
-#pragma unroll
-    for (int e = 0; e < kPer; ++e) {
-      int x, y;
-      obs_cell(n, p, r, c, x, y);
-      v[e] = ((planes[p * n + x] >> y) & 1u) ? 1.0f : 0.0f;
-      if (++c == w) {
-        c = 0;
-        if (++r == n) { r = 0; ++p; }
+  const int total = 12 * n * w;
+  // j / w by multiply-shift: with m = ceil(2^20 / w) the quotient is exact while j * (m*w - 2^20) < 2^20,
+  // i.e. for every j < 12*24*22 = 6336 and w <= 22 (j*w <= 139392 < 2^20); j*m < 2^32 as well (m <= 2^20/3 + 1)
+  const uint32_t m_row = ((1u << 20) + w - 1) / w;
+  for (int64_t env = blockIdx.x; env < count; env += gridDim.x) {
+    RecordRef<1> b{const_cast<uint32_t*>(records + env * rw), n};
+    for (int t = threadIdx.x; t < 12 * n; t += kObsThreads) {
+      const int p = t / n;
+      planes[t] = obs_plane_word(b, p, t - p * n);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 12 * n; t += kObsThreads) {
+      const int p = t / n, r = t - p * n;
+      uint32_t bits = 0;
+      if (p < 6) {  // red: (r, c) <- cell (c+1, n-1-r)
+        const int y = n - 1 - r;
+        for (int c = 0; c < w; ++c) bits |= ((planes[p * n + c + 1] >> y) & 1u) << c;
+      } else {      // blue: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column, reversed
+        bits = __brev(planes[p * n + (n - 1 - r)]) >> (32 - (n - 1));
+        bits &= (1u << w) - 1u;
       }
-      if (p >= 12) { p = 11; }  // tail of the last vector stays in bounds (never stored past total)
+      rowbits[t] = bits;
     }
-    if (kVec4) {
-      *reinterpret_cast<float4*>(dst + j) = make_float4(v[0], v[1 % kPer], v[2 % kPer], v[3 % kPer]);
-    } else {
-      dst[j] = v[0];
+    __syncthreads();
+    float* dst = out + env * static_cast<int64_t>(total);
+    constexpr int kPer = kVec4 ? 4 : 1;
+    for (int j = threadIdx.x * kPer; j < total; j += kObsThreads * kPer) {
+      int row = static_cast<int>((static_cast<uint32_t>(j) * m_row) >> 20);
+      int c = j - row * w;
+      uint32_t bits = rowbits[row] >> c;
+      float v[kPer];
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        v[e] = (bits & 1u) ? 1.0f : 0.0f;
+        bits >>= 1;
+        if (++c == w) {  // next output row (total % 4 == 0, so the last vector never runs past the end)
+          c = 0;
+          ++row;
+          bits = rowbits[min(row, 12 * n - 1)];
+        }
+      }
+      if (kVec4) {
+        *reinterpret_cast<float4*>(dst + j) = make_float4(v[0], v[1 % kPer], v[2 % kPer], v[3 % kPer]);
+      } else {
+        dst[j] = v[0];
+      }
     }
+    __syncthreads();  // planes / rowbits are rewritten for the next env
   }
 }
 
@@ -241,26 +330,31 @@ cudaError_t launch_clone(uint32_t* dst, const uint32_t* src, const int64_t* src_
 cudaError_t launch_legal_actions(const uint32_t* records, int64_t count, int n, void* out_actions, int elem_bytes,
                                  int64_t stride, int32_t* out_counts, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  const int threads = 256;
-  const int64_t blocks = (count * 32 + threads - 1) / threads;
+  const int threads = kLegalWarps * 32;
+  const unsigned blocks = static_cast<unsigned>(grid_for(count, kLegalWarps, 148 * 8));  // 8 resident blocks per SM
   const int rw = record_words(n);
   if (elem_bytes == 2)
-    legal_actions_kernel<uint16_t><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
-        records, count, n, rw, static_cast<uint16_t*>(out_actions), stride, out_counts);
+    legal_actions_kernel<uint16_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
+                                                             static_cast<uint16_t*>(out_actions), stride, out_counts);
   else if (elem_bytes == 4)
-    legal_actions_kernel<int32_t><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
-        records, count, n, rw, static_cast<int32_t*>(out_actions), stride, out_counts);
+    legal_actions_kernel<int32_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
+                                                            static_cast<int32_t*>(out_actions), stride, out_counts);
   else
-    legal_actions_kernel<int64_t><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
-        records, count, n, rw, static_cast<int64_t*>(out_actions), stride, out_counts);
+    legal_actions_kernel<int64_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
+                                                            static_cast<int64_t*>(out_actions), stride, out_counts);
   return cudaGetLastError();
 }
 
 cudaError_t launch_legal_mask(const uint32_t* records, int64_t count, int n, uint8_t* out, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  const int threads = 256;
-  const int64_t blocks = (count * 32 + threads - 1) / threads;
-  legal_mask_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(records, count, n, record_words(n), out);
+  const int threads = kLegalWarps * 32;
+  const unsigned blocks = static_cast<unsigned>(grid_for(count, kLegalWarps, 148 * 8));
+  // the fast path needs word-aligned columns (n % 4 == 0) and 16-byte aligned rows (n*n % 16 == 0 then)
+  const bool fast = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  if (fast)
+    legal_mask_kernel<true><<<blocks, threads, 0, s>>>(records, count, n, record_words(n), out);
+  else
+    legal_mask_kernel<false><<<blocks, threads, 0, s>>>(records, count, n, record_words(n), out);
   return cudaGetLastError();
 }
 
@@ -288,11 +382,11 @@ cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, fl
   if (count <= 0) return cudaSuccess;
   const int rw = record_words(n);
   const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  // grid.x is limited to 2^31-1 blocks, far above any batch that fits in HBM
+  const unsigned blocks = static_cast<unsigned>(grid_for(count, 1, 148 * 8));  // persistent: 8 blocks per SM
   if (vec)
-    observation_kernel<true><<<static_cast<unsigned>(count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+    observation_kernel<true><<<blocks, kObsThreads, 0, s>>>(records, count, n, rw, out);
   else
-    observation_kernel<false><<<static_cast<unsigned>(count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+    observation_kernel<false><<<blocks, kObsThreads, 0, s>>>(records, count, n, rw, out);
   return cudaGetLastError();
 }
 
