@@ -238,68 +238,93 @@ __global__ void query_kernel(const uint32_t* __restrict__ records, int64_t count
 // ---------------------------------------------------------- observation ---
 // TwixTState::ObservationTensor (twixt.cc:101-132): [12, n, n-2] float32 per
 // env, HBM-write bound (25 KB out per 0.9 KB in at n=24).  Persistent blocks
-// stride over the envs.  Per env: (1) the 12 planes are formed as column words
-// in BOARD coordinates (obs_plane_word), (2) re-cut into one bit-word per
-// OUTPUT row (GetTensorPosition, twixtboard.cc:590-597: red planes are a
-// transpose, blue planes a bit reversal), (3) every thread expands 4
-// consecutive output floats from those row words and stores them as a float4.
+// stride over the envs; the NEXT env's record is fetched into registers while
+// the current one is expanded, so HBM latency hides behind the float stores.
+// Per env (all from shared memory):
+//  (1) the 12 planes as column words in BOARD coordinates (obs_plane_word);
+//  (2) one bit-word per OUTPUT row (GetTensorPosition, twixtboard.cc:590-597:
+//      red rows are board rows gathered across the column words, blue rows
+//      are one column word bit-reversed);
+//  (3) the rows concatenated into one flat bit stream of 12*n*(n-2) bits;
+//  (4) each thread turns 4 consecutive stream bits into a float4 (4 | 32, so a
+//      group never straddles a word) -- no index arithmetic beyond a shift.
 constexpr int kObsThreads = 256;
 constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
+constexpr int kObsStreamWords = (12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2) + 31) / 32;
+constexpr int kObsRecordWords = kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE;  // 220 <= 256 threads
 
 template <bool kVec4>
 __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t* __restrict__ records, int64_t count,
                                                                   int n, int rw, float* __restrict__ out) {
-  __shared__ uint32_t planes[kObsPlaneWords];  // [12][n] column words, board coordinates
-  __shared__ uint32_t rowbits[kObsPlaneWords]; // [12][n] output rows, bit c = tensor column c
+  __shared__ __align__(16) uint32_t rec[kObsRecordWords + 4];  // the env's record
+  __shared__ uint32_t planes[kObsPlaneWords];                  // [12][n] column words, board coordinates
+  __shared__ uint32_t rowbits[kObsPlaneWords];                 // [12][n] output rows, bit c = tensor column c
+  __shared__ uint32_t stream[kObsStreamWords];                 // the tensor as a bit stream, output order
   const int w = n - 2;
-  const int total = 12 * n * w;
-  // j / w by multiply-shift: with m = ceil(2^20 / w) the quotient is exact while j * (m*w - 2^20) < 2^20,
-  // i.e. for every j < 12*24*22 = 6336 and w <= 22 (j*w <= 139392 < 2^20); j*m < 2^32 as well (m <= 2^20/3 + 1)
+  const int rows = 12 * n;
+  const int total = rows * w;
+  const int stream_words = (total + 31) >> 5;
+  const uint32_t wmask = (1u << w) - 1u;
+  // bit / w by multiply-shift: m = ceil(2^20 / w) is exact while x * (m*w - 2^20) < 2^20, i.e. for every
+  // x < 6336 + 32 and w <= 22; x*m < 2^32 as well (host-checked exhaustively in tests/test_abi.py)
   const uint32_t m_row = ((1u << 20) + w - 1) / w;
-  for (int64_t env = blockIdx.x; env < count; env += gridDim.x) {
-    RecordRef<1> b{const_cast<uint32_t*>(records + env * rw), n};
-    for (int t = threadIdx.x; t < 12 * n; t += kObsThreads) {
+  const int tid = threadIdx.x;
+  int64_t env = blockIdx.x;
+  uint32_t pre = (env < count && tid < rw) ? __ldg(records + env * rw + tid) : 0u;
+  for (; env < count; env += gridDim.x) {
+    if (tid < rw) rec[tid] = pre;
+    __syncthreads();
+    const int64_t next = env + gridDim.x;
+    if (next < count && tid < rw) pre = __ldg(records + next * rw + tid);  // in flight during the expansion
+    RecordRef<1> b{rec, n};
+    for (int t = tid; t < rows; t += kObsThreads) {
       const int p = t / n;
       planes[t] = obs_plane_word(b, p, t - p * n);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 12 * n; t += kObsThreads) {
+    for (int t = tid; t < rows; t += kObsThreads) {
       const int p = t / n, r = t - p * n;
       uint32_t bits = 0;
       if (p < 6) {  // red: (r, c) <- cell (c+1, n-1-r)
         const int y = n - 1 - r;
         for (int c = 0; c < w; ++c) bits |= ((planes[p * n + c + 1] >> y) & 1u) << c;
       } else {      // blue: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column, reversed
-        bits = __brev(planes[p * n + (n - 1 - r)]) >> (32 - (n - 1));
-        bits &= (1u << w) - 1u;
+        bits = (__brev(planes[p * n + (n - 1 - r)]) >> (32 - (n - 1))) & wmask;
       }
       rowbits[t] = bits;
     }
     __syncthreads();
-    float* dst = out + env * static_cast<int64_t>(total);
-    constexpr int kPer = kVec4 ? 4 : 1;
-    for (int j = threadIdx.x * kPer; j < total; j += kObsThreads * kPer) {
-      int row = static_cast<int>((static_cast<uint32_t>(j) * m_row) >> 20);
-      int c = j - row * w;
-      uint32_t bits = rowbits[row] >> c;
-      float v[kPer];
-#pragma unroll
-      for (int e = 0; e < kPer; ++e) {
-        v[e] = (bits & 1u) ? 1.0f : 0.0f;
-        bits >>= 1;
-        if (++c == w) {  // next output row (total % 4 == 0, so the last vector never runs past the end)
-          c = 0;
-          ++row;
-          bits = rowbits[min(row, 12 * n - 1)];
-        }
+    for (int k = tid; k < stream_words; k += kObsThreads) {
+      // stream bits [32k, 32k+32): the tail of one row and the heads of the following ones
+      const int bit0 = k << 5;
+      int row = static_cast<int>((static_cast<uint32_t>(bit0) * m_row) >> 20);
+      int have = 0;
+      uint32_t acc = 0;
+      int off = bit0 - row * w;  // bits of `row` already consumed by earlier words
+      while (have < 32 && row < rows) {
+        acc |= (rowbits[row] >> off) << have;
+        have += w - off;
+        off = 0;
+        ++row;
       }
-      if (kVec4) {
-        *reinterpret_cast<float4*>(dst + j) = make_float4(v[0], v[1 % kPer], v[2 % kPer], v[3 % kPer]);
-      } else {
-        dst[j] = v[0];
-      }
+      stream[k] = acc;
     }
-    __syncthreads();  // planes / rowbits are rewritten for the next env
+    __syncthreads();
+    float* dst = out + env * static_cast<int64_t>(total);
+    if (kVec4) {
+      for (int q = tid; q < (total >> 2); q += kObsThreads) {  // total % 4 == 0
+        const uint32_t b4 = stream[q >> 3] >> ((q & 7) << 2);
+        float4 v;
+        v.x = (b4 & 1u) ? 1.0f : 0.0f;
+        v.y = (b4 & 2u) ? 1.0f : 0.0f;
+        v.z = (b4 & 4u) ? 1.0f : 0.0f;
+        v.w = (b4 & 8u) ? 1.0f : 0.0f;
+        reinterpret_cast<float4*>(dst)[q] = v;
+      }
+    } else {
+      for (int j = tid; j < total; j += kObsThreads) dst[j] = ((stream[j >> 5] >> (j & 31)) & 1u) ? 1.0f : 0.0f;
+    }
+    // the next iteration's first barrier orders these reads before rec/planes/rowbits/stream are rewritten
   }
 }
 
