@@ -398,3 +398,30 @@ def test_cuda_golden_playthrough():
         if ply < 35:
             st.apply_action(pt["actions"][ply])
     assert st.is_terminal() and st.returns() == [1.0, -1.0] and st.current_player() == -4
+
+
+def test_batched_rollout_evaluator_mcts_shape(oracle_mod):
+    """BASELINE config C3: n=12 leaves at random plies x rollout_count=4; means equal the oracle's."""
+    from twixt_for_open_spiel_b200.rollout import BatchedRolloutEvaluator
+    n, B, R = 12, 256, 4
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(33)
+    leaves = []
+    for i in range(B):
+        st = og.new_initial_state()
+        st.replay(random_game_actions(og, rng, force_swap=(i % 5 == 0), max_plies=rng.randrange(0, 61)))
+        leaves.append(st)
+    ev = BatchedRolloutEvaluator(n, n_rollouts=R, max_leaves=300, seed=SEED)
+    recs = np.stack([st.export_record() for st in leaves])
+    for call in range(2):  # the second call draws fresh streams
+        ids = ev.stream_ids(B)
+        got = ev.evaluate_records(recs)
+        want = np.zeros((B, 2), dtype=np.float64)
+        for i, leaf in enumerate(leaves):
+            for r in range(R):
+                st = leaf.clone()
+                st.playout_philox(SEED, int(ids[i * R + r]))
+                want[i] += st.returns()
+        assert np.array_equal(got, (want / R).astype(np.float32)), call
+    assert np.array_equal(ev.batch.export_state(0, B), recs)  # the leaves themselves were not advanced
+    ev.close()

@@ -1,0 +1,116 @@
+// twixt_b200_game.h -- open_spiel plug-in adapter over libtwixt_b200 (C ABI in
+// include/twixt_b200.h).  Drop-in replacement for the reference's
+//   class TwixTState : public State   (open_spiel/games/twixt/twixt.h:31-112)
+//   class TwixTGame  : public Game    (twixt.h:114-146)
+// with the same short name, parameters and error texts (twixt.cc:35-58,
+// 134-145), so `LoadGame("twixt(board_size=12)")`, upstream example.cc,
+// mcts_example.cc and the game's own tests keep working while every rule
+// evaluation runs on the GPU.  One State = one env slot of a device pool owned
+// by the Game; Clone() is a device-side record copy.
+//
+// To build inside an open_spiel checkout: copy this directory to
+// open_spiel/games/twixt_b200/, add twixt_b200_game.cc to GAME_SOURCES and link
+// libtwixt_b200.so.  Here it is compile- and run-tested
+// against the minimal open_spiel header shim used by the oracle.
+#ifndef TWIXT_B200_ADAPTER_GAME_H_
+#define TWIXT_B200_ADAPTER_GAME_H_
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "open_spiel/spiel.h"
+#include "twixt_b200.h"
+
+namespace open_spiel {
+namespace twixt_b200 {
+
+inline constexpr int kNumPlayers = 2;
+inline constexpr int kDefaultBoardSize = TWIXT_DEFAULT_BOARD_SIZE;  // twixtboard.h:34
+inline constexpr bool kDefaultAnsiColorOutput = true;               // twixtboard.h:36
+inline constexpr int kDefaultPoolSize = 256;
+
+class TwixTB200Game;
+
+// Env slots of one game, grown a batch at a time.
+class EnvPool {
+ public:
+  EnvPool(int board_size, int device, int pool_size);
+  ~EnvPool();
+  struct Slot {
+    twixt_batch* batch;
+    int64_t index;
+  };
+  Slot Take();
+  void Give(Slot s);
+
+ private:
+  int board_size_, device_, pool_size_;
+  std::mutex mu_;
+  std::vector<twixt_batch*> batches_;
+  std::vector<Slot> free_;
+};
+
+class TwixTB200State : public State {
+ public:
+  explicit TwixTB200State(std::shared_ptr<const Game> game);
+  TwixTB200State(const TwixTB200State& other);
+  TwixTB200State& operator=(const TwixTB200State&) = delete;
+  ~TwixTB200State() override;
+
+  Player CurrentPlayer() const override;
+  std::string ActionToString(Player player, Action action) const override;
+  std::string ToString() const override;
+  bool IsTerminal() const override;
+  std::vector<double> Returns() const override;
+  std::string InformationStateString(Player player) const override;
+  std::string ObservationString(Player player) const override;
+  void ObservationTensor(Player player, absl::Span<float> values) const override;
+  std::unique_ptr<State> Clone() const override;
+  void UndoAction(Player, Action) override {}  // a stub in the reference too (twixt.h:84)
+  std::vector<Action> LegalActions() const override;
+
+ protected:
+  void DoApplyAction(Action action) override;
+
+ private:
+  const TwixTB200Game& parent() const;
+  EnvPool::Slot slot_;
+};
+
+class TwixTB200Game : public Game {
+ public:
+  explicit TwixTB200Game(const GameParameters& params);
+
+  std::unique_ptr<State> NewInitialState() const override {
+    return std::unique_ptr<State>(new TwixTB200State(shared_from_this()));
+  }
+  int NumDistinctActions() const override { return info_.num_distinct_actions; }
+  int NumPlayers() const override { return kNumPlayers; }
+  double MinUtility() const override { return info_.min_utility; }
+  absl::optional<double> UtilitySum() const override { return info_.utility_sum; }
+  double MaxUtility() const override { return info_.max_utility; }
+  std::vector<int> ObservationTensorShape() const override {
+    return {info_.obs_shape[0], info_.obs_shape[1], info_.obs_shape[2]};  // per game, not a function-static
+  }
+  int MaxGameLength() const { return info_.max_game_length; }
+  bool ansi_color_output() const { return ansi_color_output_; }
+  int board_size() const { return board_size_; }
+  EnvPool& pool() const { return *pool_; }
+
+ private:
+  bool ansi_color_output_;
+  int board_size_;
+  twixt_game_info info_;
+  std::unique_ptr<EnvPool> pool_;
+};
+
+// The picture of Board::ToString (twixtboard.cc:278-448) from a state record.
+std::string RenderRecord(const uint32_t* record, int board_size, bool ansi_color_output);
+
+}  // namespace twixt_b200
+}  // namespace open_spiel
+
+#endif  // TWIXT_B200_ADAPTER_GAME_H_
