@@ -130,9 +130,18 @@ static int LegalActionsTest() {  // twixt_test.cc:133-183
   EXPECT(state->ActionToString(0, 19) == "xc5" && state->ActionToString(1, 43) == "of5");  // twixtboard.h:166-167
   std::vector<float> obs(576);
   state->ObservationTensor(0, absl::Span<float>(obs.data(), obs.size()));
-  int ones = 0;
-  for (float v : obs) ones += v == 1.0f;
-  EXPECT(ones >= 9);
+  // the oracle's tensor for this position: exactly these seven 1.0s
+  const int want_ones[] = {170, 192, 205, 226, 301, 306, 519};
+  size_t k = 0;
+  for (size_t i = 0; i < obs.size(); ++i) {
+    if (obs[i] == 1.0f) {
+      EXPECT(k < 7 && static_cast<int>(i) == want_ones[k]);
+      ++k;
+    } else {
+      EXPECT(obs[i] == 0.0f);
+    }
+  }
+  EXPECT(k == 7);
   return 0;
 }
 
