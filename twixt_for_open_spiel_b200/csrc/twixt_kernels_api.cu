@@ -87,10 +87,14 @@ __device__ __forceinline__ uint32_t legal_word_of(const LegalInputs& in, int n, 
   return play & ~(in.red | in.blue);
 }
 
-// popc + warp prefix sum give every column its offset in the ascending list
-// (action = x*n + y is column-major, twixtboard.cc:603-605); each lane expands
-// its column into a shared-memory row, then the warp streams the row out with
-// coalesced (vector) stores.
+// The legal cells of an env form one n*n-bit string in action order (action =
+// x*n + y is column-major, twixtboard.cc:603-605).  It is cut into 32 equal
+// chunks of ceil(n*n/32) <= 18 bits, one per lane, so all 32 lanes carry the
+// same load whatever the board size (a chunk spans at most two column words,
+// fetched from their lanes by shuffle).  popc + warp prefix sum give every
+// chunk its offset in the ascending list; each lane expands its chunk into a
+// shared-memory row, then the warp streams the row out with coalesced vector
+// stores.
 template <typename T>
 __global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
     const uint32_t* __restrict__ records, int64_t count, int n, int rw, T* __restrict__ out_actions, int64_t stride,
@@ -101,12 +105,21 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
   int64_t env = blockIdx.x * static_cast<int64_t>(kLegalWarps) + warp;
   if (env >= count) return;  // whole warp leaves together
   T* row = rows[warp];
+  // this lane's chunk of the flat cell string: cells [first, first + chunk_bits)
+  const int cells = n * n;
+  const int chunk_bits = (cells + 31) >> 5;
+  const int first = lane * chunk_bits;
+  const int x0 = min(first / n, n - 1), y0 = first - (first / n) * n;
+  const int x1 = min(x0 + 1, n - 1);
+  const uint32_t chunk_mask = first >= cells ? 0u : ((1u << min(chunk_bits, cells - first)) - 1u);
   LegalInputs cur = legal_fetch(records + env * rw, n, lane);
   for (; env < count; env += nwarps) {
     const int64_t next = env + nwarps;
     LegalInputs nxt = cur;
     if (next < count) nxt = legal_fetch(records + next * rw, n, lane);
-    const uint32_t w = legal_word_of(cur, n, lane);
+    const uint32_t colw = legal_word_of(cur, n, lane);
+    const uint32_t w0 = __shfl_sync(kFullMask, colw, x0), w1 = __shfl_sync(kFullMask, colw, x1);
+    const uint32_t w = ((w0 >> y0) | (w1 << (n - y0))) & chunk_mask;
     const int c = __popc(w);
     int incl = c;
 #pragma unroll
@@ -117,13 +130,18 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
     const int total = __shfl_sync(kFullMask, incl, 31);
     if (out_counts != nullptr && lane == 0) out_counts[env] = total;
     if (out_actions != nullptr) {
+      // this chunk's cells, filled from both ends at once (two independent chains per trip; with one
+      // bit left both ends name the same slot and value); flat cell index == action
       uint32_t rest = w;
-      int r = incl - c;
-      const int base = lane * n;
-      while (rest) {  // ascending rows of this column
-        const int y = __ffs(static_cast<int>(rest)) - 1;
+      T* lo = row + (incl - c);
+      T* hi = row + incl;
+      while (rest) {
+        const int b0 = __ffs(static_cast<int>(rest)) - 1;
+        const int b1 = 31 - __clz(static_cast<int>(rest));
         rest &= rest - 1u;
-        row[r++] = static_cast<T>(base + y);
+        rest &= ~(1u << b1);
+        *lo++ = static_cast<T>(first + b0);
+        *--hi = static_cast<T>(first + b1);
       }
       __syncwarp();
       T* dst = out_actions + env * stride;
