@@ -363,6 +363,8 @@ class TwixTBatch {
     a.out_actions = static_cast<uint16_t*>(act.dev);
     a.trace_plies = out_actions ? trace_plies : 0;
     a.stats = d_stats_;
+    a.tickets = &d_stats_->tickets;
+    TW_CUDA(cudaMemsetAsync(&d_stats_->tickets, 0, sizeof(unsigned long long), stream_));
     TW_CUDA(launch_playout(a, stream_));
     launches_ += 1;
     TW_TRY(Finish(&ret));

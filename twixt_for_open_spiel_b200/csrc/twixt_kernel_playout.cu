@@ -19,11 +19,16 @@
 //    one MOVE for the lanes without flood work and one flood VISIT for the
 //    lanes with it, instead of 31 lanes idling through one lane's whole flood;
 //    the flood stack lives in shared memory next to the planes;
-//  * candidate links are handled direction-major (place_peg).
+//  * candidate links are handled direction-major and branch-free (place_peg);
+//  * lanes are PERSISTENT: games end at different plies (250..573 at n=24), so
+//    a lane whose game is over writes its env back and takes the next env of
+//    the range from a ticket counter instead of idling until the slowest game
+//    of its warp ends.
 // Shared memory per env: planes 0..7 (pegs, links, border flags) + the flood
 // stack + a per-column count cache that replaces the 24-word legal scan by 6
-// bytewise words (twixt_engine.cuh, count_cache_*).  The "blocked neighbour" plane is write-only for the rules, so it
-// stays in HBM and is OR-ed in place on the rare blocked link.
+// bytewise words (twixt_engine.cuh, count_cache_*).  The "blocked neighbour"
+// plane is write-only for the rules, so it stays in HBM and is OR-ed in place
+// (RED.OR, fire-and-forget) on a blocked link.
 //
 // Reference loop reproduced: upstream example.cc / RandomRolloutEvaluator
 // (LegalActions -> uniform pick -> ApplyAction until IsTerminal), with the
@@ -41,53 +46,33 @@ namespace twixt {
 namespace {
 
 constexpr int kPlayoutThreads = 128;  // 4 warps per block
+constexpr int kSmemPlanes = 8;        // P_RED .. P_END
+constexpr int kStackWords = 24;       // flood stack entries (one per word)
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
-// Two placements of the env state during a playout (template parameter SP =
-// number of leading planes staged in shared memory):
-//   SP = 8  all planes the rules read (pegs, links, border flags) on chip;
-//           888 B per env at n=24 -> 256 envs = 8 warps per SM
-//   SP = 2  only the two peg planes (touched by every move) on chip, links and
-//           border flags are read/written in place in HBM/L2 (a move fetches its
-//           whole 5-column link window with independent loads, one round trip);
-//           264 B per env at n=24 -> 768 envs = 24 warps per SM to hide latency
-template <int SP>
-struct PlayoutCfg {
-  static constexpr int kStackWords = SP >= 8 ? 24 : 12;  // flood stack entries (one per word)
-  __host__ __device__ static constexpr int words(int n) { return SP * n + kStackWords + kCacheWords; }
-};
+__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
 
-// The env's planes: the first SP in shared memory (stride 32 words), the rest in its HBM record.
-template <int NT, int SP>
+// The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
+template <int NT>
 struct PlayoutRef {
   uint32_t* p;     // smem, this lane's column
-  uint32_t* gpl;   // global: the record's plane words (record + kHeaderWords)
+  uint32_t* gblk;  // global: the record's P_BLOCKED words
   int n_rt;
   __device__ __forceinline__ int n() const { return NT > 0 ? NT : n_rt; }
-  __device__ __forceinline__ uint32_t ld(int plane, int col) const {
-    return plane < SP ? p[(plane * n() + col) * 32] : gpl[plane * n() + col];
-  }
-  __device__ __forceinline__ void st(int plane, int col, uint32_t v) {
-    if (plane < SP) p[(plane * n() + col) * 32] = v;
-    else gpl[plane * n() + col] = v;
-  }
+  __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
+  __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
   __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
-  // peg planes are always on chip
-  __device__ __forceinline__ uint32_t ld_pegs(int plane, int col) const { return p[(plane * n() + col) * 32]; }
-  __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
-  __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const {
-    return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld_pegs(plane, col) : 0u;
-  }
+  __device__ __forceinline__ uint32_t ld_pegs(int plane, int col) const { return ld(plane, col); }
+  __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { st(plane, col, v); }
+  __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
-  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gpl + P_BLOCKED * n() + col, bits); }
+  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
   // per-column count cache (twixt_engine.cuh, count_cache_*), after the planes and the stack
   static constexpr bool kCountCache = true;
-  __device__ __forceinline__ uint32_t* cache_word(int i) const {
-    return p + (SP * n() + PlayoutCfg<SP>::kStackWords + i) * 32;
-  }
+  __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
   __device__ __forceinline__ uint32_t cache_ld(int i) const { return *cache_word(i); }
   __device__ __forceinline__ void cache_st(int i, uint32_t v) { *cache_word(i) = v; }
   __device__ __forceinline__ void note_peg(int x, int y, int delta) {
@@ -97,63 +82,114 @@ struct PlayoutRef {
   }
 };
 
-template <int CAP>
 struct SmemStack {
   uint32_t* base;  // smem, this lane's column of the stack words
   int sp;
   bool overflow;
   __device__ __forceinline__ bool empty() const { return sp == 0; }
   __device__ __forceinline__ void push(uint32_t c) {
-    if (sp < CAP) base[(sp++) * 32] = c;
+    if (sp < kStackWords) base[(sp++) * 32] = c;
     else overflow = true;
   }
   __device__ __forceinline__ uint32_t pop() { return base[(--sp) * 32]; }
 };
 
-template <int NT, int SP>
+template <int NT>
 __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutArgs a) {
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
   const int n = NT > 0 ? NT : a.n;
   const int rw = record_words(n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
-  const bool active = idx < a.count;
-  uint32_t* mine = smem + warp * (PlayoutCfg<SP>::words(n) * 32) + lane;
-  uint32_t* grec = a.records + idx * rw;
-  const int staged_pairs = (SP * n) / 2;  // staged plane words, as 8-byte pieces (planes start 16-byte aligned)
-
-  Header h;
-  h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
-  if (active) {
-    const uint4 hw = *reinterpret_cast<const uint4*>(grec);
-    unpack_header(hw.x, hw.y, hw.z, hw.w, h);
-    const uint2* src = reinterpret_cast<const uint2*>(grec + kHeaderWords);
-    for (int q = 0; q < staged_pairs; ++q) {
-      const uint2 v = src[q];
-      mine[(2 * q + 0) * 32] = v.x;
-      mine[(2 * q + 1) * 32] = v.y;
-    }
-  }
-  // every thread only ever touches its own column of the staging buffer: no barrier needed
-
-  PlayoutRef<NT, SP> b{mine, grec + kHeaderWords, n};
-  SmemStack<PlayoutCfg<SP>::kStackWords> stk{mine + SP * n * 32, 0, false};
-  if (active) count_cache_build(b);
-  const uint32_t swapped_before = h.swapped;
-  const bool open_at_start = active && h.result == kOpen;
-
-  const uint64_t stream =
-      !active ? 0ull : (a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx));
-  const uint32_t s_lo = static_cast<uint32_t>(stream), s_hi = static_cast<uint32_t>(stream >> 32);
+  uint32_t* mine = smem + warp * (playout_words(n) * 32) + lane;
+  const int plane_quads = (kSmemPlanes * n) / 4;  // 8n staged words = 2n 16-byte pieces (planes start 16-byte aligned)
   const uint32_t k_lo = static_cast<uint32_t>(a.seed), k_hi = static_cast<uint32_t>(a.seed >> 32);
 
-  uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  // ---- per-lane state of the env being played ------------------------------
+  int64_t idx = -1;  // env held by this lane (index within the range), -1 = none
+  uint32_t* grec = nullptr;
+  Header h;
+  h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
+  PlayoutRef<NT> b{mine, nullptr, n};
+  SmemStack stk{mine + kSmemPlanes * n * 32, 0, false};
+  uint32_t s_lo = 0, s_hi = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0;
   int step = 0;
-  uint32_t pend = 0, origin = 0;
+  uint32_t pend = 0, origin = 0, swapped_before = 0;
   int fplane = P_START;
-  bool playing = open_at_start && a.max_plies > 0;
-  while (__any_sync(kFullMask, playing || pend != 0u || !stk.empty())) {
+  bool playing = false, open_at_start = false;
+  // ---- per-lane totals over all envs this lane plays -------------------------
+  uint32_t t_plies = 0, t_games = 0, t_red = 0, t_blue = 0, t_draws = 0, t_swaps = 0, t_maxlen = 0;
+
+  // Take env `e` of the range: copy its planes into this lane's column of shared memory.
+  auto take = [&](int64_t e) {
+    idx = e;
+    grec = a.records + e * rw;
+    const uint4* src = reinterpret_cast<const uint4*>(grec);
+    const uint4 hw = src[0];
+    unpack_header(hw.x, hw.y, hw.z, hw.w, h);
+    for (int q = 0; q < plane_quads; ++q) {
+      const uint4 v = src[1 + q];
+      mine[(4 * q + 0) * 32] = v.x;
+      mine[(4 * q + 1) * 32] = v.y;
+      mine[(4 * q + 2) * 32] = v.z;
+      mine[(4 * q + 3) * 32] = v.w;
+    }
+    b.gblk = grec + kHeaderWords + P_BLOCKED * n;
+    count_cache_build(b);
+    const uint64_t stream = a.stream_ids != nullptr ? a.stream_ids[e] : a.stream_base + static_cast<uint64_t>(e);
+    s_lo = static_cast<uint32_t>(stream);
+    s_hi = static_cast<uint32_t>(stream >> 32);
+    step = 0;
+    pend = 0;
+    stk.sp = 0;
+    stk.overflow = false;
+    swapped_before = h.swapped;
+    open_at_start = h.result == kOpen;
+    playing = open_at_start && a.max_plies > 0;
+  };
+
+  // Give the env back: final planes + header to HBM, per-env outputs, lane totals.
+  auto give = [&]() {
+    uint4* dst = reinterpret_cast<uint4*>(grec);
+    uint4 hw;
+    pack_header(h, hw.x, hw.y, hw.z, hw.w);
+    dst[0] = hw;
+    for (int q = 0; q < plane_quads; ++q) {
+      uint4 v;
+      v.x = mine[(4 * q + 0) * 32];
+      v.y = mine[(4 * q + 1) * 32];
+      v.z = mine[(4 * q + 2) * 32];
+      v.w = mine[(4 * q + 3) * 32];
+      dst[1 + q] = v;
+    }
+    if (a.out_returns != nullptr) {
+      const float r = h.result == kRedWin ? 1.0f : (h.result == kBlueWin ? -1.0f : 0.0f);
+      reinterpret_cast<float2*>(a.out_returns)[idx] = make_float2(r, r == 0.0f ? 0.0f : -r);
+    }
+    if (a.out_lengths != nullptr) a.out_lengths[idx] = step;
+    t_plies += static_cast<uint32_t>(step);
+    if (open_at_start && h.result != kOpen) {
+      t_games += 1;
+      t_red += h.result == kRedWin;
+      t_blue += h.result == kBlueWin;
+      t_draws += h.result == kDraw;
+      t_maxlen = max(t_maxlen, h.ply);
+    }
+    t_swaps += h.swapped != swapped_before;
+    idx = -1;
+  };
+
+  // every thread only ever touches its own column of the staging buffer: no barrier needed anywhere.
+  // Tickets: the first gridDim.x*blockDim.x envs are pre-assigned, the rest are handed out by a counter.
+  const int64_t preassigned = static_cast<int64_t>(gridDim.x) * kPlayoutThreads;
+  bool exhausted = false;
+  {
+    const int64_t e = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
+    if (e < a.count) take(e);
+    else exhausted = true;
+  }
+
+  while (__any_sync(kFullMask, idx >= 0)) {
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
       if ((step & 3) == 0) {
@@ -187,33 +223,30 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
         stk.overflow = false;
       }
     }
-  }
-
-  if (active) {
-    uint4 hw;
-    pack_header(h, hw.x, hw.y, hw.z, hw.w);
-    *reinterpret_cast<uint4*>(grec) = hw;
-    uint2* dst = reinterpret_cast<uint2*>(grec + kHeaderWords);
-    for (int q = 0; q < staged_pairs; ++q) dst[q] = make_uint2(mine[(2 * q + 0) * 32], mine[(2 * q + 1) * 32]);
-    if (a.out_returns != nullptr) {
-      const float r = h.result == kRedWin ? 1.0f : (h.result == kBlueWin ? -1.0f : 0.0f);
-      reinterpret_cast<float2*>(a.out_returns)[idx] = make_float2(r, r == 0.0f ? 0.0f : -r);
+    // ---- RETIRE + REFILL: a finished env goes back to HBM, the lane takes the next one
+    if (idx >= 0 && !playing && pend == 0u && stk.empty()) {
+      give();
+      if (!exhausted) {
+        const int64_t e = preassigned + static_cast<int64_t>(atomicAdd(a.tickets, 1ull));
+        if (e < a.count) take(e);
+        else exhausted = true;
+      }
     }
-    if (a.out_lengths != nullptr) a.out_lengths[idx] = step;
   }
 
   // batch statistics: warp-reduce, one atomic per warp and counter
   if (a.stats != nullptr) {
-    const bool finished = open_at_start && h.result != kOpen;
-    unsigned long long plies = static_cast<unsigned long long>(step);
-    for (int o = 16; o > 0; o >>= 1) plies += __shfl_xor_sync(kFullMask, plies, o);
-    const unsigned games = __popc(__ballot_sync(kFullMask, finished));
-    const unsigned red = __popc(__ballot_sync(kFullMask, finished && h.result == kRedWin));
-    const unsigned blue = __popc(__ballot_sync(kFullMask, finished && h.result == kBlueWin));
-    const unsigned draws = __popc(__ballot_sync(kFullMask, finished && h.result == kDraw));
-    const unsigned swaps = __popc(__ballot_sync(kFullMask, active && h.swapped != swapped_before));
-    unsigned maxlen = finished ? h.ply : 0u;
-    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(kFullMask, maxlen, o));
+    unsigned long long plies = t_plies;
+    unsigned games = t_games, red = t_red, blue = t_blue, draws = t_draws, swaps = t_swaps, maxlen = t_maxlen;
+    for (int o = 16; o > 0; o >>= 1) {
+      plies += __shfl_xor_sync(kFullMask, plies, o);
+      games += __shfl_xor_sync(kFullMask, games, o);
+      red += __shfl_xor_sync(kFullMask, red, o);
+      blue += __shfl_xor_sync(kFullMask, blue, o);
+      draws += __shfl_xor_sync(kFullMask, draws, o);
+      swaps += __shfl_xor_sync(kFullMask, swaps, o);
+      maxlen = max(maxlen, __shfl_xor_sync(kFullMask, maxlen, o));
+    }
     if (lane == 0) {
       if (plies) atomicAdd(&a.stats->plies, plies);
       if (games) atomicAdd(&a.stats->games, static_cast<unsigned long long>(games));
@@ -226,58 +259,54 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   }
 }
 
-int g_smem_planes = 8;  // TWIXT_PLAYOUT_SMEM_PLANES=2|8 (experiments); see PlayoutCfg
+int g_num_sms = 0;
 
-template <int NT, int SP>
+template <int NT>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * PlayoutCfg<SP>::words(a.n) * sizeof(uint32_t);
-  const int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
-  playout_kernel<NT, SP><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(a.n) * sizeof(uint32_t);
+  // persistent grid: as many blocks as fit on the device at once (or fewer for small ranges)
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, playout_kernel<NT>, kPlayoutThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
+  const int64_t resident = static_cast<int64_t>(g_num_sms > 0 ? g_num_sms : 148) * per_sm;
+  if (blocks > resident) blocks = resident;
+  playout_kernel<NT><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
-template <int NT, int SP>
+template <int NT>
 cudaError_t setup_nt(int n_for_size) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * PlayoutCfg<SP>::words(n_for_size) * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(playout_kernel<NT, SP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
-}
-
-template <int SP>
-cudaError_t launch_sp(const PlayoutArgs& a, cudaStream_t s) {
-  switch (a.n) {
-    case 8: return launch_nt<8, SP>(a, s);
-    case 12: return launch_nt<12, SP>(a, s);
-    case 24: return launch_nt<24, SP>(a, s);
-    default: return launch_nt<0, SP>(a, s);
-  }
-}
-
-template <int SP>
-cudaError_t setup_sp() {
-  cudaError_t e;
-  if ((e = setup_nt<0, SP>(24)) != cudaSuccess) return e;
-  if ((e = setup_nt<8, SP>(8)) != cudaSuccess) return e;
-  if ((e = setup_nt<12, SP>(12)) != cudaSuccess) return e;
-  return setup_nt<24, SP>(24);
 }
 
 }  // namespace
 
 cudaError_t playout_setup() {
-  const char* v = getenv("TWIXT_PLAYOUT_SMEM_PLANES");
-  if (v != nullptr && (v[0] == '2' || v[0] == '8')) g_smem_planes = v[0] - '0';
-  cudaError_t e = setup_sp<8>();
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  return setup_sp<2>();
+  if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = setup_nt<0>(24)) != cudaSuccess) return e;
+  if ((e = setup_nt<8>(8)) != cudaSuccess) return e;
+  if ((e = setup_nt<12>(12)) != cudaSuccess) return e;
+  return setup_nt<24>(24);
 }
 
 cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s) {
   if (a.count <= 0) return cudaSuccess;
-  return g_smem_planes == 2 ? launch_sp<2>(a, s) : launch_sp<8>(a, s);
+  switch (a.n) {
+    case 8: return launch_nt<8>(a, s);
+    case 12: return launch_nt<12>(a, s);
+    case 24: return launch_nt<24>(a, s);
+    default: return launch_nt<0>(a, s);
+  }
 }
 
 }  // namespace twixt

@@ -20,6 +20,8 @@ struct DeviceStats {
   // apply kernel, 0xFFFFFFFF = none
   unsigned int illegal_index;
   unsigned int pad;
+  // ticket counter of the persistent playout kernel (zeroed before every launch)
+  unsigned long long tickets;
 };
 
 struct PlayoutArgs {
@@ -35,6 +37,7 @@ struct PlayoutArgs {
   uint16_t* out_actions;       // [trace_plies, count] or nullptr
   int trace_plies;
   DeviceStats* stats;
+  unsigned long long* tickets;  // &stats->tickets
 };
 
 cudaError_t launch_reset(uint32_t* records, int64_t count, int n, cudaStream_t s);
