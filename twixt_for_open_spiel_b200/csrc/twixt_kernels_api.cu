@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
 // [count, n*n] uint8 mask.  For n % 4 == 0 every lane turns its column word into n mask bytes with the
 // nibble-spreading multiply (4 bits -> 4 bytes), the warp stages the n*n bytes in shared memory and
 // writes them out with 16-byte stores; other sizes take the byte-wise path.
-template <bool kFast>
+// kWords = n/4 fixed at compile time for the fast path (0 = byte-wise path for any n).
+template <int kWords>
 __global__ void __launch_bounds__(kLegalWarps * 32) legal_mask_kernel(const uint32_t* __restrict__ records,
                                                                       int64_t count, int n, int rw,
                                                                       uint8_t* __restrict__ out) {
@@ -181,16 +182,18 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_mask_kernel(const uint
     if (next < count) nxt = legal_fetch(records + next * rw, n, lane);
     const uint32_t w = legal_word_of(cur, n, lane);
     uint8_t* dst = out + env * cells;
-    if (kFast) {
-      if (lane < n) {
-        const int words = n >> 2;
-        for (int q = 0; q < words; ++q)  // bits 4q..4q+3 -> one byte each
-          row[lane * words + q] = (((w >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
+    if (kWords > 0) {
+      if (lane < 4 * kWords) {
+#pragma unroll
+        for (int q = 0; q < kWords; ++q)  // bits 4q..4q+3 -> one byte each
+          row[lane * kWords + q] = (((w >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
       }
       __syncwarp();
-      const int nvec = cells >> 4;  // n % 4 == 0  =>  n*n % 16 == 0
-      for (int v = lane; v < nvec; v += 32)
-        reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(row)[v];
+      constexpr int kVecs = kWords * kWords;  // n*n/16 with n = 4*kWords
+#pragma unroll
+      for (int v = 0; v < (kVecs + 31) / 32; ++v)
+        if (v * 32 + lane < kVecs)
+          reinterpret_cast<uint4*>(dst)[v * 32 + lane] = reinterpret_cast<const uint4*>(row)[v * 32 + lane];
       __syncwarp();
     } else {
       for (int base = 0; base < cells; base += 32) {
@@ -394,10 +397,15 @@ cudaError_t launch_legal_mask(const uint32_t* records, int64_t count, int n, uin
   const unsigned blocks = static_cast<unsigned>(grid_for(count, kLegalWarps, 148 * 8));
   // the fast path needs word-aligned columns (n % 4 == 0) and 16-byte aligned rows (n*n % 16 == 0 then)
   const bool fast = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-  if (fast)
-    legal_mask_kernel<true><<<blocks, threads, 0, s>>>(records, count, n, record_words(n), out);
-  else
-    legal_mask_kernel<false><<<blocks, threads, 0, s>>>(records, count, n, record_words(n), out);
+  const int rw = record_words(n);
+  switch (fast ? n / 4 : 0) {
+    case 2: legal_mask_kernel<2><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    case 3: legal_mask_kernel<3><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    case 4: legal_mask_kernel<4><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    case 5: legal_mask_kernel<5><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    case 6: legal_mask_kernel<6><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    default: legal_mask_kernel<0><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+  }
   return cudaGetLastError();
 }
 
