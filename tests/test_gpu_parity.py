@@ -425,3 +425,44 @@ def test_batched_rollout_evaluator_mcts_shape(oracle_mod):
         assert np.array_equal(got, (want / R).astype(np.float32)), call
     assert np.array_equal(ev.batch.export_state(0, B), recs)  # the leaves themselves were not advanced
     ev.close()
+
+
+def test_full_size_playout_properties(oracle_mod):
+    """BASELINE config C4 at full size (n=24, 1 Mi envs): size-independent properties plus an oracle-replayed
+    sample spread over the whole range, determinism, and independence of how the range is sharded."""
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    n, E = 24, 1 << 20
+    batch = TwixTBatch(n, E, 0, SEED)
+    rets, lens, _ = batch.playout()
+    st = batch.stats()
+    assert st["games"] == E and st["plies"] == int(lens.astype(np.int64).sum())
+    assert bool(batch.is_terminal().all()) and (batch.current_player() == -4).all()
+    assert int(lens.max()) == st["max_length"] <= n * n - 3 and int(lens.min()) >= 2 * (n - 1) // 2
+    red, blue = int((rets[:, 0] > 0).sum()), int((rets[:, 1] > 0).sum())
+    assert (red, blue, E - red - blue) == (st["red_wins"], st["blue_wins"], st["draws"])
+    assert np.array_equal(rets[:, 0], -rets[:, 1])  # zero-sum, twixt.h:128
+    assert 0.07 < red / E < 0.15 and 0.07 < blue / E < 0.15  # SURVEY section 6: ~0.10 / 0.13 / 0.77
+    cnt = batch.legal_actions(0, 4096)[1]
+    assert (cnt == 0).all()  # LegalActions() of a terminal state is empty (twixt.h:87-88)
+    # an oracle-replayed sample across the range (first, last, and a stride in between)
+    og = oracle_mod.OracleGame(n)
+    sample = sorted(set([0, 1, 31, 32, 127, 128, E - 1, E - 129] + list(range(7, E, E // 300))))
+    recs = {e: batch.export_state(e, 1)[0] for e in sample}
+    for e in sample:
+        s = og.new_initial_state()
+        acts = s.playout_philox(SEED, e)
+        assert len(acts) == lens[e] and s.returns() == rets[e].tolist(), e
+        assert np.array_equal(recs[e], s.export_record()), e
+    # determinism: the same seed replays the same games
+    batch.reset()
+    rets2, lens2, _ = batch.playout()
+    assert np.array_equal(lens, lens2) and np.array_equal(rets, rets2)
+    # sharding independence: a shard playing global ids [a, a+m) alone gives the same games
+    a, m = 3 * (E // 8) + 5, 10_000
+    shard = TwixTBatch(n, m, 0, SEED)
+    shard.set_stream_base(a)
+    srets, slens, _ = shard.playout()
+    assert np.array_equal(slens, lens[a:a + m]) and np.array_equal(srets, rets[a:a + m])
+    assert np.array_equal(shard.export_state(0, 64), batch.export_state(a, 64))
+    shard.close()
+    batch.close()
