@@ -240,24 +240,38 @@ TW_HD uint32_t links_of(const B& b, int x, int y) {
 // making 31 lanes wait for one lane's whole flood.
 //
 // One visit: pop a cell, flag + push every linked neighbour that lacks the flag.
+// Straight-line over the eight directions (loads of all eight neighbour flag
+// words, predicated stores/pushes): eight data-dependent branches per visit
+// cost more in branch resolution than the few instructions they skip.
 template <class B, class Stack>
 TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
   const uint32_t c = stk.pop();
   const int cx = static_cast<int>(c >> 8), cy = static_cast<int>(c & 255u);
   const uint32_t lm = links_of(b, cx, cy);
+  // flag words of the columns cx-2 .. cx+2 (index = dx + 2); column cx itself is never a neighbour
+  uint32_t f[5];
+  f[0] = b.ld_guard(flag_plane, cx - 2);
+  f[1] = b.ld_guard(flag_plane, cx - 1);
+  f[2] = 0u;
+  f[3] = b.ld_guard(flag_plane, cx + 1);
+  f[4] = b.ld_guard(flag_plane, cx + 2);
+  uint32_t add[5] = {0u, 0u, 0u, 0u, 0u};  // flag bits to set per column
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int d = 0; d < 8; ++d) {
-    if ((lm >> d) & 1u) {
-      const int tx = cx + dir_dx(d), ty = cy + dir_dy(d);
-      const uint32_t f = b.ld(flag_plane, tx);
-      if (!((f >> ty) & 1u)) {
-        b.st(flag_plane, tx, f | (1u << ty));
-        stk.push(static_cast<uint32_t>((tx << 8) | ty));
-      }
-    }
+    const int dx = dir_dx(d), dy = dir_dy(d);
+    const bool linked = (lm >> d) & 1u;
+    const int ty = linked ? cy + dy : 0;  // keeps the shift count in range when there is no link
+    const bool need = linked && !((f[dx + 2] >> ty) & 1u);
+    add[dx + 2] |= need ? (1u << ty) : 0u;
+    if (need) stk.push(static_cast<uint32_t>(((cx + dx) << 8) | ty));
   }
+  // two directions share each neighbour column, so the stores come after all eight tests
+  if (add[0]) b.st(flag_plane, cx - 2, f[0] | add[0]);
+  if (add[1]) b.st(flag_plane, cx - 1, f[1] | add[1]);
+  if (add[3]) b.st(flag_plane, cx + 1, f[3] | add[3]);
+  if (add[4]) b.st(flag_plane, cx + 2, f[4] | add[4]);
 }
 
 // If the stack overflowed, the dropped cells are recovered by closing the

@@ -23,7 +23,8 @@
 //  * lanes are PERSISTENT: games end at different plies (250..573 at n=24), so
 //    a lane whose game is over writes its env back and takes the next env of
 //    the range from a ticket counter instead of idling until the slowest game
-//    of its warp ends.
+//    of its warp ends; the new env arrives by cp.async (LDGSTS) while the rest
+//    of the warp keeps playing.
 // Shared memory per env: planes 0..7 (pegs, links, border flags) + the flood
 // stack + a per-column count cache that replaces the 24-word legal scan by 6
 // bytewise words (twixt_engine.cuh, count_cache_*).  The "blocked neighbour"
@@ -33,9 +34,9 @@
 // Reference loop reproduced: upstream example.cc / RandomRolloutEvaluator
 // (LegalActions -> uniform pick -> ApplyAction until IsTerminal), with the
 // per-move semantics of twixtboard.cc:457-499.
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "twixt_engine.cuh"
 #include "twixt_kernels.cuh"
@@ -120,32 +121,36 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   // ---- per-lane totals over all envs this lane plays -------------------------
   uint32_t t_plies = 0, t_games = 0, t_red = 0, t_blue = 0, t_draws = 0, t_swaps = 0, t_maxlen = 0;
 
-  // Take env `e` of the range: copy its planes into this lane's column of shared memory.
-  auto take = [&](int64_t e) {
+  // Taking env `e` of the range is split in two so that its HBM latency overlaps the other lanes' work:
+  // begin_take issues asynchronous global->shared copies (cp.async, 4 bytes each: the destination is this
+  // lane's strided column) of the header (parked in the idle flood-stack words) and the planes;
+  // finish_take runs at the top of the next loop iteration, when the data has normally arrived.
+  bool loading = false;
+  auto begin_take = [&](int64_t e) {
     idx = e;
     grec = a.records + e * rw;
-    const uint4* src = reinterpret_cast<const uint4*>(grec);
-    const uint4 hw = src[0];
-    unpack_header(hw.x, hw.y, hw.z, hw.w, h);
-    for (int q = 0; q < plane_quads; ++q) {
-      const uint4 v = src[1 + q];
-      mine[(4 * q + 0) * 32] = v.x;
-      mine[(4 * q + 1) * 32] = v.y;
-      mine[(4 * q + 2) * 32] = v.z;
-      mine[(4 * q + 3) * 32] = v.w;
-    }
-    b.gblk = grec + kHeaderWords + P_BLOCKED * n;
-    count_cache_build(b);
-    const uint64_t stream = a.stream_ids != nullptr ? a.stream_ids[e] : a.stream_base + static_cast<uint64_t>(e);
-    s_lo = static_cast<uint32_t>(stream);
-    s_hi = static_cast<uint32_t>(stream >> 32);
-    step = 0;
+    for (int w = 0; w < kHeaderWords; ++w) __pipeline_memcpy_async(stk.base + w * 32, grec + w, 4);
+    for (int w = 0; w < kSmemPlanes * n; ++w) __pipeline_memcpy_async(mine + w * 32, grec + kHeaderWords + w, 4);
+    __pipeline_commit();
+    loading = true;
+    playing = false;
     pend = 0;
     stk.sp = 0;
     stk.overflow = false;
+  };
+  auto finish_take = [&]() {
+    __pipeline_wait_prior(0);
+    unpack_header(stk.base[0], stk.base[32], stk.base[64], stk.base[96], h);
+    b.gblk = grec + kHeaderWords + P_BLOCKED * n;
+    count_cache_build(b);
+    const uint64_t stream = a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx);
+    s_lo = static_cast<uint32_t>(stream);
+    s_hi = static_cast<uint32_t>(stream >> 32);
+    step = 0;
     swapped_before = h.swapped;
     open_at_start = h.result == kOpen;
     playing = open_at_start && a.max_plies > 0;
+    loading = false;
   };
 
   // Give the env back: final planes + header to HBM, per-env outputs, lane totals.
@@ -185,11 +190,12 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   bool exhausted = false;
   {
     const int64_t e = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
-    if (e < a.count) take(e);
+    if (e < a.count) begin_take(e);
     else exhausted = true;
   }
 
   while (__any_sync(kFullMask, idx >= 0)) {
+    if (loading) finish_take();
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
       if ((step & 3) == 0) {
@@ -224,11 +230,11 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
       }
     }
     // ---- RETIRE + REFILL: a finished env goes back to HBM, the lane takes the next one
-    if (idx >= 0 && !playing && pend == 0u && stk.empty()) {
+    if (idx >= 0 && !loading && !playing && pend == 0u && stk.empty()) {
       give();
       if (!exhausted) {
         const int64_t e = preassigned + static_cast<int64_t>(atomicAdd(a.tickets, 1ull));
-        if (e < a.count) take(e);
+        if (e < a.count) begin_take(e);
         else exhausted = true;
       }
     }
