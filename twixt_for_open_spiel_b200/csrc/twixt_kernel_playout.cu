@@ -113,7 +113,13 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
   PlayoutRef<NT> b{mine, nullptr, n};
   SmemStack stk{mine + kSmemPlanes * n * 32, 0, false};
-  uint32_t s_lo = 0, s_hi = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  uint32_t s_lo = 0, s_hi = 0;
+  // Random words: block `rq` (moves 4rq..4rq+3) in ra[], block rq+1 in rb[].  Lanes of a warp are at
+  // different move numbers, so blocks are produced on a warp-uniform schedule (every 4th iteration, all
+  // lanes together) instead of whenever a lane runs dry, which would run the Philox rounds divergently in
+  // nearly every iteration.  A lane makes at most one move per iteration, so two blocks always suffice.
+  uint32_t ra[4] = {0, 0, 0, 0}, rb[4] = {0, 0, 0, 0};
+  uint32_t rq = 0;
   int step = 0;
   uint32_t pend = 0, origin = 0, swapped_before = 0;
   int fplane = P_START;
@@ -147,6 +153,9 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
     s_lo = static_cast<uint32_t>(stream);
     s_hi = static_cast<uint32_t>(stream >> 32);
     step = 0;
+    rq = 0;
+    philox4x32_10(s_lo, s_hi, 0u, 0u, k_lo, k_hi, ra);
+    philox4x32_10(s_lo, s_hi, 1u, 0u, k_lo, k_hi, rb);
     swapped_before = h.swapped;
     open_at_start = h.result == kOpen;
     playing = open_at_start && a.max_plies > 0;
@@ -194,16 +203,21 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
     else exhausted = true;
   }
 
-  while (__any_sync(kFullMask, idx >= 0)) {
+  for (uint32_t it = 1; __any_sync(kFullMask, idx >= 0); ++it) {
     if (loading) finish_take();
+    if ((it & 3u) == 0u) {  // warp-uniform: every lane that has moved into its second block gets the next one
+      if (static_cast<uint32_t>(step) >= 4u * (rq + 1u)) {
+        rq += 1u;
+        ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2]; ra[3] = rb[3];
+        philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
+      }
+    }
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
-      if ((step & 3) == 0) {
-        uint32_t r[4];
-        philox4x32_10(s_lo, s_hi, static_cast<uint32_t>(step) >> 2, 0u, k_lo, k_hi, r);
-        r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3];
-      }
-      const uint32_t word = (step & 2) ? ((step & 1) ? r3 : r2) : ((step & 1) ? r1 : r0);
+      const uint32_t rel = static_cast<uint32_t>(step) - 4u * rq;  // 0..7: position in the two blocks
+      const uint32_t wa = (rel & 2u) ? ((rel & 1u) ? ra[3] : ra[2]) : ((rel & 1u) ? ra[1] : ra[0]);
+      const uint32_t wb = (rel & 2u) ? ((rel & 1u) ? rb[3] : rb[2]) : ((rel & 1u) ? rb[1] : rb[0]);
+      const uint32_t word = (rel & 4u) ? wb : wa;
       const int L = legal_count(h, n);
       const int k = static_cast<int>(playout_index(word, static_cast<uint32_t>(L)));
       int x, y;
