@@ -466,3 +466,56 @@ def test_full_size_playout_properties(oracle_mod):
     assert np.array_equal(shard.export_state(0, 64), batch.export_state(a, 64))
     shard.close()
     batch.close()
+
+
+def test_playout_edge_cases(oracle_mod):
+    """Ragged ranges, zero budgets, already-terminal envs, truncated traces, device-side stream ids."""
+    import torch
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    n, E = 7, 333  # not a multiple of the block or warp size
+    og = oracle_mod.OracleGame(n)
+    batch = TwixTBatch(n, E, 0, SEED)
+    # max_plies = 0: nothing moves
+    init = batch.export_state()
+    rets, lens, _ = batch.playout(max_plies=0)
+    assert (lens == 0).all() and (rets == 0).all() and np.array_equal(batch.export_state(), init)
+    assert batch.stats()["plies"] == 0 and batch.stats()["games"] == 0
+    # a sub-range in the middle, budget 5, trace shorter than the budget
+    rets, lens, trace = batch.playout(100, 37, max_plies=5, out_actions=np.zeros((3, 37), dtype=np.uint16))
+    assert (lens == 5).all() and trace.shape == (3, 37)
+    after = batch.export_state()
+    assert np.array_equal(after[:100], init[:100]) and np.array_equal(after[137:], init[137:])
+    for j in range(37):
+        st = og.new_initial_state()
+        acts = st.playout_philox(SEED, 100 + j, 5)
+        assert trace[:, j].tolist() == acts[:3]
+        assert np.array_equal(after[100 + j], st.export_record())
+    # finish everything; envs 100..136 continue from ply 5 with fresh step counters
+    ids = torch.arange(1000, 1000 + E, dtype=torch.int64, device="cuda:0")
+    rets_d = torch.zeros((E, 2), dtype=torch.float32, device="cuda:0")
+    lens_d = torch.zeros(E, dtype=torch.int32, device="cuda:0")
+    batch.playout(stream_ids=ids, out_returns=rets_d, out_lengths=lens_d)
+    batch.synchronize()
+    final = batch.export_state()
+    for e in (0, 99, 100, 136, 137, 332):
+        st = og.new_initial_state()
+        if 100 <= e < 137:
+            st.playout_philox(SEED, e, 5)
+        acts = st.playout_philox(SEED, 1000 + e)
+        assert int(lens_d[e]) == len(acts) and np.array_equal(final[e], st.export_record()), e
+        assert rets_d[e].tolist() == st.returns()
+    # everything is terminal now: another playout is a no-op and counts no games
+    before = batch.stats()
+    rets3, lens3, _ = batch.playout()
+    assert (lens3 == 0).all() and np.array_equal(rets3, rets_d.cpu().numpy())
+    assert batch.stats()["games"] == before["games"] and np.array_equal(batch.export_state(), final)
+    # int32 legal lists with a wide stride; untouched tail keeps its fill value
+    batch.reset(0, 10)
+    la = np.full((10, 60), -7, dtype=np.int32)
+    cnt = np.zeros(10, dtype=np.int32)
+    batch.legal_actions(0, 10, out_actions=la, out_counts=cnt)
+    assert (cnt == n * (n - 2)).all() and (la[:, n * (n - 2):] == -7).all()
+    assert la[0, :n * (n - 2)].tolist() == og.new_initial_state().legal_actions()
+    with pytest.raises(ValueError):
+        batch.legal_actions(0, 10, out_actions=np.zeros((10, 5), dtype=np.int64))  # stride too small
+    batch.close()
