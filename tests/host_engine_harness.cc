@@ -116,7 +116,9 @@ int he_playout(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int max_pli
   return step;
 }
 
-// The same playout with the count cache and the move / flood-visit interleaving of the CUDA kernel.
+// The same playout with the structure of the CUDA kernel: per-column count cache, moves interleaved with
+// single flood visits, two buffered Philox blocks refreshed on a fixed 4-iteration schedule, and the
+// selection of move i+1 issued (speculatively) between the placement and the link evaluation of move i.
 int he_playout_cached(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int max_plies, int64_t* actions_out) {
   CachedRec b;
   b.p = rec;
@@ -124,27 +126,43 @@ int he_playout_cached(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int 
   Header h;
   load_header(b, h);
   count_cache_build(b);
+  const uint32_t s_lo = static_cast<uint32_t>(stream), s_hi = static_cast<uint32_t>(stream >> 32);
+  const uint32_t k_lo = static_cast<uint32_t>(seed), k_hi = static_cast<uint32_t>(seed >> 32);
   int step = 0;
-  uint32_t r[4] = {0, 0, 0, 0};
+  uint32_t ra[4], rb[4], rq = 0;
+  philox4x32_10(s_lo, s_hi, 0u, 0u, k_lo, k_hi, ra);
+  philox4x32_10(s_lo, s_hi, 1u, 0u, k_lo, k_hi, rb);
+  auto word_at = [&](uint32_t index) {
+    const uint32_t rel = index - 4u * rq;
+    return rel < 4u ? ra[rel] : rb[rel - 4u];
+  };
   uint32_t pend = 0, origin = 0;
   int fplane = P_START;
   LocalStack<TW_TEST_STACK> stk;
   bool playing = h.result == kOpen && max_plies > 0;
-  while (playing || pend != 0u || !stk.empty()) {
+  int sx = 0, sy = 0;
+  if (playing) select_legal(b, h, static_cast<int>(playout_index(word_at(0), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
+  for (uint32_t it = 1; playing || pend != 0u || !stk.empty(); ++it) {
+    if ((it & 3u) == 0u && static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {
+      rq += 1u;
+      for (int i = 0; i < 4; ++i) ra[i] = rb[i];
+      philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
+    }
     if (playing && pend == 0u && stk.empty()) {
-      if ((step & 3) == 0)
-        philox4x32_10(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
-                      static_cast<uint32_t>(step) >> 2, 0u, static_cast<uint32_t>(seed),
-                      static_cast<uint32_t>(seed >> 32), r);
-      int L = legal_count(h, n);
-      int k = static_cast<int>(playout_index(r[step & 3], static_cast<uint32_t>(L)));
-      int x, y;
-      select_legal(b, h, k, x, y);
-      if (actions_out) actions_out[step] = x * n + y;
-      apply_begin(b, h, x, y, pend);
-      origin = static_cast<uint32_t>((x << 8) | y);
+      if (actions_out) actions_out[step] = sx * n + sy;
+      const Placement pl = begin_move(b, h, sx, sy);
+      Header hn = h;  // the position the following move is chosen in, if this move does not end the game
+      hn.ply = h.ply + 1u;
+      const int ln = legal_count(hn, n);
+      int nx, ny;
+      select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
+      const bool win = link_move<true>(b, pl, pend);
+      finish_move(h, pl, win);
+      origin = static_cast<uint32_t>((pl.x << 8) | pl.y);
       ++step;
       playing = h.result == kOpen && step < max_plies;
+      sx = nx;
+      sy = ny;
     }
     if (stk.empty() && pend != 0u) {
       const bool start = (pend & kFloodStart) != 0u;

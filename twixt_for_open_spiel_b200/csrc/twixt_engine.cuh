@@ -315,38 +315,75 @@ TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y
 
 enum : uint32_t { kFloodStart = 1u, kFloodEnd = 2u };
 
-// SetPegAndLinks (twixtboard.cc:501-571) for a peg of `player` on the empty
-// cell (x,y), WITHOUT the flood: `pending` receives kFloodStart / kFloodEnd for
-// the floods the caller still has to run from (x,y) (twixtboard.cc:558-570).
-// Returns true iff the new peg is now linked to both of its owner's border
-// lines (the win test of UpdateResult, twixtboard.cc:194-199).
-// The eight directions are handled direction-major with compile-time offsets
-// and crossing masks, so lanes of a warp that link in the same direction stay
-// converged.
+// A move is evaluated in three pieces so that the fused playout kernel can
+// overlap the middle one with the selection of the following move:
+//   begin_move   swap handling, the peg itself, the counters, and the mask of
+//                own-colour pegs a knight's move away (the link candidates)
+//   link_move    SetPegAndLinks' link part (twixtboard.cc:510-556): crossing
+//                tests, links / blocked flags, inherited border flags
+//   finish_move  move counter, first-move bookkeeping, result (192-207)
+struct Placement {
+  int x, y;        // where the peg went (differs from the action's cell after a swap)
+  int player;
+  uint32_t cand;   // Compass-ordered 8-bit mask of own-colour knight neighbours
+  uint32_t action; // the action as played
+};
+
 template <class B>
-TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pending) {
+TW_HD Placement begin_move(B& b, Header& h, int x, int y) {
   const int n = b.n();
-  const int own = player == kRed ? P_RED : P_BLUE;
-  const uint32_t bit = 1u << y;
-  b.st_pegs(own, x, b.ld_pegs(own, x) | bit);
+  Placement p;
+  p.player = static_cast<int>(h.ply & 1u);
+  p.action = static_cast<uint32_t>(x * n + y);
+  if (h.ply == 1u && p.action == h.move_one) {
+    // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
+    // on the cell turned by 90 degrees (471-473)
+    b.st_pegs(P_RED, x, b.ld_pegs(P_RED, x) & ~(1u << y));
+    b.note_peg(x, y, -1);
+    b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
+    b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
+    h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
+    h.cnt[kBlue] += (y >= 1 && y <= n - 2) ? 1 : 0;
+    h.swapped = 1u;
+    const int rx = y, ry = n - 1 - x;
+    x = rx;
+    y = ry;
+  }
+  p.x = x;
+  p.y = y;
+  const int own = p.player == kRed ? P_RED : P_BLUE;
+  b.st_pegs(own, x, b.ld_pegs(own, x) | (1u << y));
   b.note_peg(x, y, +1);
   h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
   h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
-
-  // border flags the cell has by position (twixtboard.cc:223-231); a peg can
-  // only stand on its owner's border lines
-  bool to_start = player == kRed ? (y == 0) : (x == 0);
-  bool to_end = player == kRed ? (y == n - 1) : (x == n - 1);
-  bool neutral = false, new_links = false;
-
   // own-colour pegs a knight's move away, as a Compass-ordered 8-bit mask
   const uint32_t e1 = b.ld_pegs_guard(own, x + 1), e2 = b.ld_pegs_guard(own, x + 2);
   const uint32_t w1 = b.ld_pegs_guard(own, x - 1), w2 = b.ld_pegs_guard(own, x - 2);
-  const uint32_t cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
-                        ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) |
-                        ((((w2 << 1) >> y) & 1u) << 5) | (((w2 >> (y + 1)) & 1u) << 6) |
-                        (((w1 >> (y + 2)) & 1u) << 7);
-  if (cand) {
+  p.cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
+           ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) | ((((w2 << 1) >> y) & 1u) << 5) |
+           (((w2 >> (y + 1)) & 1u) << 6) | (((w1 >> (y + 2)) & 1u) << 7);
+  return p;
+}
+
+// Returns true iff the new peg is now linked to both of its owner's border
+// lines (the win test of UpdateResult, twixtboard.cc:194-199); `pending`
+// receives kFloodStart / kFloodEnd for the floods the caller still has to run
+// from the peg (twixtboard.cc:558-570).  Straight-line code: the eight
+// directions are handled direction-major with compile-time offsets and crossing
+// masks, all inputs fetched up front by independent loads; kAlways = true drops
+// even the `any candidate?` branch so the whole function is one basic block.
+template <bool kAlways, class B>
+TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
+  const int n = b.n();
+  const int x = p.x, y = p.y;
+  const uint32_t bit = 1u << y;
+  // border flags the cell has by position (twixtboard.cc:223-231); a peg can
+  // only stand on its owner's border lines
+  bool to_start = p.player == kRed ? (y == 0) : (x == 0);
+  bool to_end = p.player == kRed ? (y == n - 1) : (x == n - 1);
+  bool neutral = false, new_links = false;
+  const uint32_t cand = p.cand;
+  if (kAlways || cand) {
     // everything the eight directions may read, fetched with independent loads
     LinkWindow lw;
     uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
@@ -396,6 +433,13 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
   return to_start && to_end;
 }
 
+TW_HD void finish_move(Header& h, const Placement& p, bool win) {
+  if (h.ply == 0u) h.move_one = p.action;
+  h.ply += 1u;
+  if (win) h.result = p.player == kRed ? kRedWin : kBlueWin;   // twixtboard.cc:194-199
+  else if (h.cnt[1 - p.player] == 0) h.result = kDraw;         // 203-206
+}
+
 // Board::ApplyAction (twixtboard.cc:457-499) for an action known to be legal,
 // given as its cell (x,y) (action == x*n+y), up to but excluding the border-
 // flag floods: on return (x,y) is the cell the peg went to (it differs from the
@@ -404,28 +448,11 @@ TW_HD bool place_peg(B& b, Header& h, int player, int x, int y, uint32_t& pendin
 // own flags), so the header is final.
 template <class B>
 TW_HD void apply_begin(B& b, Header& h, int& x, int& y, uint32_t& pending) {
-  const int n = b.n();
-  const int player = static_cast<int>(h.ply & 1u);
-  const uint32_t action = static_cast<uint32_t>(x * n + y);
-  if (h.ply == 1u && action == h.move_one) {
-    // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
-    // on the cell turned by 90 degrees (471-473)
-    b.st_pegs(P_RED, x, b.ld_pegs(P_RED, x) & ~(1u << y));
-    b.note_peg(x, y, -1);
-    b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
-    b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
-    h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
-    h.cnt[kBlue] += (y >= 1 && y <= n - 2) ? 1 : 0;
-    h.swapped = 1u;
-    const int rx = y, ry = n - 1 - x;
-    x = rx;
-    y = ry;
-  }
-  const bool win = place_peg(b, h, player, x, y, pending);
-  if (h.ply == 0u) h.move_one = action;
-  h.ply += 1u;
-  if (win) h.result = player == kRed ? kRedWin : kBlueWin;     // twixtboard.cc:194-199
-  else if (h.cnt[1 - player] == 0) h.result = kDraw;           // 203-206
+  const Placement p = begin_move(b, h, x, y);
+  const bool win = link_move<false>(b, p, pending);
+  finish_move(h, p, win);
+  x = p.x;
+  y = p.y;
 }
 
 // The complete move (apply kernel, host tests).
@@ -534,9 +561,11 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
   }
   // first byte whose inclusive prefix exceeds sk
   const uint32_t gt = bytes_gt(sp, bytes4(static_cast<uint32_t>(sk)));
-  const int j = tw_ctz(gt) >> 3;
+  // (gt == 0 only when there is no legal cell at all -- a speculative selection whose result is never
+  // used; the clamps keep its loads inside the board)
+  const int j = gt ? (tw_ctz(gt) >> 3) : 0;
   const int before = j == 0 ? 0 : static_cast<int>((sp >> (8 * (j - 1))) & 0xFFu);
-  const int x = 4 * si + j;
+  const int x = (4 * si + j) < n ? (4 * si + j) : (n - 1);
   out_x = x;
   out_y = select_bit(legal_word(b, h, x), sk - before);
 }

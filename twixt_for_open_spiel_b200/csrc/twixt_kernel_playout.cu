@@ -120,6 +120,15 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   // nearly every iteration.  A lane makes at most one move per iteration, so two blocks always suffice.
   uint32_t ra[4] = {0, 0, 0, 0}, rb[4] = {0, 0, 0, 0};
   uint32_t rq = 0;
+  auto word_at = [&](uint32_t index) {  // random word of move `index`, 4rq <= index < 4rq + 8
+    const uint32_t rel = index - 4u * rq;
+    const uint32_t wa = (rel & 2u) ? ((rel & 1u) ? ra[3] : ra[2]) : ((rel & 1u) ? ra[1] : ra[0]);
+    const uint32_t wb = (rel & 2u) ? ((rel & 1u) ? rb[3] : rb[2]) : ((rel & 1u) ? rb[1] : rb[0]);
+    return (rel & 4u) ? wb : wa;
+  };
+  // The cell of the NEXT move is chosen one move ahead: between placing a peg and evaluating its links
+  // (two independent dependency chains the scheduler can interleave), see the MOVE section.
+  int sx = 0, sy = 0;
   int step = 0;
   uint32_t pend = 0, origin = 0, swapped_before = 0;
   int fplane = P_START;
@@ -159,6 +168,8 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
     swapped_before = h.swapped;
     open_at_start = h.result == kOpen;
     playing = open_at_start && a.max_plies > 0;
+    if (playing)
+      select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
     loading = false;
   };
 
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
   for (uint32_t it = 1; __any_sync(kFullMask, idx >= 0); ++it) {
     if (loading) finish_take();
     if ((it & 3u) == 0u) {  // warp-uniform: every lane that has moved into its second block gets the next one
-      if (static_cast<uint32_t>(step) >= 4u * (rq + 1u)) {
+      if (static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {  // step+1 = next word to be consumed
         rq += 1u;
         ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2]; ra[3] = rb[3];
         philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
@@ -214,20 +225,23 @@ __global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutA
     }
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
-      const uint32_t rel = static_cast<uint32_t>(step) - 4u * rq;  // 0..7: position in the two blocks
-      const uint32_t wa = (rel & 2u) ? ((rel & 1u) ? ra[3] : ra[2]) : ((rel & 1u) ? ra[1] : ra[0]);
-      const uint32_t wb = (rel & 2u) ? ((rel & 1u) ? rb[3] : rb[2]) : ((rel & 1u) ? rb[1] : rb[0]);
-      const uint32_t word = (rel & 4u) ? wb : wa;
-      const int L = legal_count(h, n);
-      const int k = static_cast<int>(playout_index(word, static_cast<uint32_t>(L)));
-      int x, y;
-      select_legal(b, h, k, x, y);
       if (a.out_actions != nullptr && step < a.trace_plies)
-        a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(x * n + y);
-      apply_begin(b, h, x, y, pend);
-      origin = static_cast<uint32_t>((x << 8) | y);
+        a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(sx * n + sy);
+      const Placement pl = begin_move(b, h, sx, sy);
+      // choose the following move now (speculatively: unused if this move ends the game); it only reads the
+      // peg planes and the count cache, which begin_move has just brought up to date
+      Header hn = h;
+      hn.ply = h.ply + 1u;
+      const int ln = legal_count(hn, n);
+      int nx, ny;
+      select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
+      const bool win = link_move<true>(b, pl, pend);
+      finish_move(h, pl, win);
+      origin = static_cast<uint32_t>((pl.x << 8) | pl.y);
       ++step;
       playing = h.result == kOpen && step < a.max_plies;
+      sx = nx;
+      sy = ny;
     }
     // ---- FLOOD: one visit for the lanes that owe border-flag propagation -----
     if (stk.empty() && pend != 0u) {
