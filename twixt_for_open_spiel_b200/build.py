@@ -20,7 +20,7 @@ SOURCES = ["twixt_kernels_api.cu", "twixt_kernel_playout.cu", "twixt_batch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("TWIXT_NVCC_EXTRA", "").split()  # experiments only (e.g. -DTW_X=1)
 
 
 def _nvcc() -> str:

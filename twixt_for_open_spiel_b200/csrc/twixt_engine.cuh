@@ -96,6 +96,10 @@ struct RecordRef {
   TW_HD void set_word(int w, uint32_t v) { p[w * kStride] = v; }
   TW_HD uint32_t ld(int plane, int col) const { return p[(kHeaderWords + plane * n() + col) * kStride]; }
   TW_HD void st(int plane, int col, uint32_t v) { p[(kHeaderWords + plane * n() + col) * kStride] = v; }
+  // conditional store; `col` may be outside the board when `c` is false
+  TW_HD void st_if(bool c, int plane, int col, uint32_t v) {
+    if (c) st(plane, col, v);
+  }
   // column outside the board reads as empty
   TW_HD uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
@@ -122,6 +126,9 @@ struct LocalStack {
   TW_HD void push(uint32_t c) {
     if (sp < kCap) v[sp++] = static_cast<uint16_t>(c);
     else overflow = true;
+  }
+  TW_HD void push_if(bool c, uint32_t cell) {
+    if (c) push(cell);
   }
   TW_HD uint32_t pop() { return v[--sp]; }
 };
@@ -265,13 +272,13 @@ TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
     const int ty = linked ? cy + dy : 0;  // keeps the shift count in range when there is no link
     const bool need = linked && !((f[dx + 2] >> ty) & 1u);
     add[dx + 2] |= need ? (1u << ty) : 0u;
-    if (need) stk.push(static_cast<uint32_t>(((cx + dx) << 8) | ty));
+    stk.push_if(need, static_cast<uint32_t>(((cx + dx) << 8) | ty));
   }
   // two directions share each neighbour column, so the stores come after all eight tests
-  if (add[0]) b.st(flag_plane, cx - 2, f[0] | add[0]);
-  if (add[1]) b.st(flag_plane, cx - 1, f[1] | add[1]);
-  if (add[3]) b.st(flag_plane, cx + 1, f[3] | add[3]);
-  if (add[4]) b.st(flag_plane, cx + 2, f[4] | add[4]);
+  b.st_if(add[0] != 0u, flag_plane, cx - 2, f[0] | add[0]);
+  b.st_if(add[1] != 0u, flag_plane, cx - 1, f[1] | add[1]);
+  b.st_if(add[3] != 0u, flag_plane, cx + 1, f[3] | add[3]);
+  b.st_if(add[4] != 0u, flag_plane, cx + 2, f[4] | add[4]);
 }
 
 // If the stack overflowed, the dropped cells are recovered by closing the
@@ -387,6 +394,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
     // everything the eight directions may read, fetched with independent loads
     LinkWindow lw;
     uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
+    uint32_t blk[3] = {0u, 0u, 0u};  // new blocked-east bits of columns x, x-1, x-2
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -410,25 +418,32 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
       // the link named by its west endpoint (x+ow, wy) and east direction de
       const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
       const bool blocked = crossing_blocked(lw, ow, wy, de);
-      if (is_cand && blocked) {
-        // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
-        // pointing east is ever read (twixtcell.h:82-84) and it always lands on
-        // the west endpoint
-        b.or_blocked(x + ow, 1u << wy);
-      }
+      // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
+      // pointing east is ever read (twixtcell.h:82-84) and it always lands on
+      // the west endpoint, i.e. in column x, x-1 or x-2 (index -ow)
+      blk[-ow] |= (is_cand && blocked) ? (1u << wy) : 0u;
       const bool make = is_cand && !blocked;
       // each direction owns a distinct (plane, column) word, and links made
       // earlier in this move never cross later ones (they share the new peg)
-      if (make) b.st(P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
+      b.st_if(make, P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
       const bool ts = (fs[dx + 2] >> ty) & 1u, te = (fe[dx + 2] >> ty) & 1u;
       new_links |= make;
       to_start |= make && ts;                // twixtboard.cc:538-540
       to_end |= make && !ts && te;           // 541-543
       neutral |= make && !ts && !te;         // 544-546
     }
+    if (blk[0] | blk[1] | blk[2]) {  // rare enough to branch around
+      if (blk[0]) b.or_blocked(x, blk[0]);
+      if (blk[1]) b.or_blocked(x - 1, blk[1]);
+      if (blk[2]) b.or_blocked(x - 2, blk[2]);
+    }
+    // the new peg's own flag words are fs[2] / fe[2]
+    b.st_if(to_start, P_START, x, fs[2] | bit);
+    b.st_if(to_end, P_END, x, fe[2] | bit);
+  } else {
+    b.st_if(to_start, P_START, x, b.ld(P_START, x) | bit);
+    b.st_if(to_end, P_END, x, b.ld(P_END, x) | bit);
   }
-  if (to_start) b.st(P_START, x, b.ld(P_START, x) | bit);
-  if (to_end) b.st(P_END, x, b.ld(P_END, x) | bit);
   pending = (new_links && neutral) ? ((to_start ? kFloodStart : 0u) | (to_end ? kFloodEnd : 0u)) : 0u;
   return to_start && to_end;
 }
