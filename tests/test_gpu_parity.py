@@ -519,3 +519,24 @@ def test_playout_edge_cases(oracle_mod):
     with pytest.raises(ValueError):
         batch.legal_actions(0, 10, out_actions=np.zeros((10, 5), dtype=np.int64))  # stride too small
     batch.close()
+
+
+def test_serialize_roundtrip_and_record_import(oracle_mod):
+    """history (de)serialisation and packed-record import give the same state."""
+    from twixt_for_open_spiel_b200 import load_game
+    game = load_game("twixt(board_size=9)")
+    og = oracle_mod.OracleGame(9)
+    rng = random.Random(9)
+    acts = random_game_actions(og, rng, force_swap=True, max_plies=40)
+    st = game.new_initial_state()
+    for a in acts:
+        st.apply_action(a)
+    again = game.deserialize_state(st.serialize())
+    from_rec = game.new_state_from_record(st.export_record())
+    ref = og.new_initial_state()
+    ref.replay(acts)
+    for s in (st, again, from_rec):
+        assert np.array_equal(s.export_record(), ref.export_record())
+        assert s.legal_actions() == ref.legal_actions() and s.current_player() == ref.current_player()
+    assert again.history() == acts and st.to_string() == again.to_string()
+    assert "[swapped]" in st.to_string()

@@ -128,6 +128,20 @@ class TwixTGame:
             return "twixt()"
         return "twixt(%s)" % ",".join("%s=%s" % (k, self._params[k]) for k in sorted(self._params))
 
+    # -- serialisation (upstream serialises a state as its action history) --------
+    def deserialize_state(self, text: str) -> "TwixTState":
+        """Inverse of TwixTState.serialize(): replays the action history on the device."""
+        state = self.new_initial_state()
+        for tok in text.replace(",", " ").split():
+            state.apply_action(int(tok))
+        return state
+
+    def new_state_from_record(self, record) -> "TwixTState":
+        """A state from an exported packed record (twixt_import_state); its history is unknown."""
+        pool, idx = self._take_slot()
+        pool.import_state(np.ascontiguousarray(record, dtype=np.uint32), idx)
+        return TwixTState(self, pool, idx, history=None)
+
     # -- slot pool -------------------------------------------------------------
     def _take_slot(self):
         if not self._free:
@@ -212,6 +226,10 @@ class TwixTState:
 
     def history_str(self) -> str:
         return ", ".join(str(a) for a in self._history)
+
+    def serialize(self) -> str:
+        """One action per line, like upstream State::Serialize() for a game without chance nodes."""
+        return "\n".join(str(a) for a in self._history)
 
     def is_chance_node(self) -> bool:
         return False
