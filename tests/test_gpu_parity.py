@@ -6,6 +6,7 @@ every ply: the ascending legal-action list, the legal mask, current player,
 terminal flag, returns, the observation tensor and the complete packed state
 record (pegs, links, blocked flags, border flags, counters).
 """
+import os
 import random
 
 import numpy as np
@@ -540,3 +541,36 @@ def test_serialize_roundtrip_and_record_import(oracle_mod):
         assert s.legal_actions() == ref.legal_actions() and s.current_player() == ref.current_player()
     assert again.history() == acts and st.to_string() == again.to_string()
     assert "[swapped]" in st.to_string()
+
+
+def test_playout_flood_stack_overflow_path_on_device(oracle_mod, tmp_path):
+    """The flood stack of the playout kernel overflows in ~1 of 10^4 floods (24 entries); a variant build with
+    a 4-entry stack makes the closure fallback run constantly, and the games must still match the oracle."""
+    import subprocess
+    import sys
+    import textwrap
+    from twixt_for_open_spiel_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    variant = build.build(out=os.path.join(root, "tests", "_build", "libtwixt_b200_stack4.so"),
+                          extra_flags=["-DTW_PLAYOUT_STACK_WORDS=4"])
+    code = textwrap.dedent("""
+        import sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        from oracle import pyoracle
+        from twixt_for_open_spiel_b200 import TwixTBatch
+        n, E, seed = 24, 1500, 0x7477697854
+        b = TwixTBatch(n, E, 0, seed)
+        rets, lens, trace = b.playout(trace=True)
+        recs = b.export_state()
+        og = pyoracle.OracleGame(n)
+        for e in range(E):
+            st = og.new_initial_state()
+            acts = st.playout_philox(seed, e)
+            assert trace[:lens[e], e].tolist() == acts, e
+            assert np.array_equal(recs[e], st.export_record()), e
+        print("variant ok")
+    """ % root)
+    env = dict(os.environ, TWIXT_B200_LIB=variant)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert res.returncode == 0 and "variant ok" in res.stdout, res.stderr[-2000:]

@@ -88,6 +88,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("TWIXT_B200_LIB")  # tests only: a variant build of the same sources
+    if override:
+        lib = C.CDLL(override)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
     if not os.path.exists(_build.LIB) or (os.environ.get("TWIXT_B200_REBUILD") == "1"):
         _build.build(force=True)
     elif _build.needs_build():

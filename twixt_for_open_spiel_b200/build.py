@@ -51,15 +51,20 @@ def needs_build() -> bool:
         return f.read().strip() != _fingerprint()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, extra_flags=()) -> str:
+    """Build the library.  `out` / `extra_flags` build a VARIANT elsewhere (tests use it to shrink the
+    playout kernel's flood stack so that its overflow path runs); the default build is the product."""
+    variant = out is not None
+    lib = out if variant else LIB
+    obj_dir = (os.path.splitext(out)[0] + "_obj") if variant else OBJ_DIR
+    if not variant and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
@@ -69,13 +74,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
-    with open(os.path.join(OBJ_DIR, "fingerprint"), "w") as f:
-        f.write(_fingerprint())
-    return LIB
+    if not variant:
+        with open(os.path.join(OBJ_DIR, "fingerprint"), "w") as f:
+            f.write(_fingerprint())
+    return lib
 
 
 if __name__ == "__main__":

@@ -48,7 +48,10 @@ namespace {
 
 constexpr int kPlayoutThreads = 128;  // 4 warps per block
 constexpr int kSmemPlanes = 8;        // P_RED .. P_END
-constexpr int kStackWords = 24;       // flood stack entries (one per word)
+#ifndef TW_PLAYOUT_STACK_WORDS
+#define TW_PLAYOUT_STACK_WORDS 24
+#endif
+constexpr int kStackWords = TW_PLAYOUT_STACK_WORDS;  // flood stack entries (one per word; tests build with 4)
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
