@@ -214,6 +214,13 @@ def kernel_microbench(torch, TwixTBatch, board_size, device, peak_gbs):
     bytes_unit = (2 * ((n * n + 7) // 8) + 16) + 4 + 2 * mean_l
     out["legal_list"] = {"envs_per_s": E / t, "ms": t * 1e3, "algo_bytes_per_env": bytes_unit,
                          "achieved_gbs": E * bytes_unit / t / 1e9, "frac": E * bytes_unit / t / 1e9 / peak_gbs}
+    # the same list as int64 (open_spiel::Action), what a drop-in LegalActions() binding asks for
+    acts64 = torch.zeros((E, b.max_legal_actions), dtype=torch.int64, device=dev)
+    t = timed(lambda: b.legal_actions(out_actions=acts64, out_counts=cnts))
+    bytes_unit = (2 * ((n * n + 7) // 8) + 16) + 4 + 8 * mean_l
+    out["legal_list_i64"] = {"envs_per_s": E / t, "ms": t * 1e3, "algo_bytes_per_env": bytes_unit,
+                             "achieved_gbs": E * bytes_unit / t / 1e9, "frac": E * bytes_unit / t / 1e9 / peak_gbs}
+    del acts64
     mask = torch.zeros((E, n * n), dtype=torch.uint8, device=dev)
     t = timed(lambda: b.legal_mask(out=mask))
     bytes_unit = (2 * ((n * n + 7) // 8) + 16) + n * n
