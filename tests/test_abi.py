@@ -92,3 +92,27 @@ def test_product_never_imports_the_oracle():
                     text = f.read()
                 assert "pyoracle" not in text and "twixt_oracle" not in text and "liboracle" not in text, fn
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+
+
+def test_header_is_plain_c_and_links():
+    """The FFI boundary: a C99 program including only include/twixt_b200.h builds, links and runs."""
+    import subprocess
+    from twixt_for_open_spiel_b200 import _lib
+    _lib.load()
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.join(ROOT, "twixt_for_open_spiel_b200")
+    exe = os.path.join(here, "_build", "abi_c_smoke")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(here, "abi_c_smoke.c"), "-o", exe, "-L", pkg, "-ltwixt_b200",
+                           "-Wl,-rpath," + pkg])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.startswith("OK"), (res.returncode, res.stdout, res.stderr)
+
+
+def test_observation_index_arithmetic_is_exact():
+    """The multiply-shift division used by the observation kernel (bit / (n-2)) is exact on its whole range."""
+    for w in range(3, 23):
+        m = ((1 << 20) + w - 1) // w
+        for j in range(0, 12 * 24 * 22 + 64):
+            assert (j * m) >> 20 == j // w and j * m < 2 ** 32
