@@ -370,7 +370,7 @@ def run_ours(args):
             "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
             "peak_source": peak_src + " (burst copy figure)",
             "algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP, "steps_per_launch": plies_per_launch,
-            "kernel_ms": k_ms,
+            "kernel_ms": k_ms, "kernel_ms_median": statistics.median(kernel_ms), "kernel_ms_best": min(kernel_ms),
             "note": "convention of SURVEY 8(d): state streamed once per move; the kernel keeps state on chip, "
                     "true DRAM traffic is ~2 records per GAME, so frac>1 is expected and the real limiter is "
                     "issue slots / shared memory (see profiles/)",
