@@ -550,12 +550,9 @@ TW_HD void count_cache_build(B& b) {
   }
 }
 
-// legal cells per column of the player to move, four columns per word
-template <class B>
-TW_HD uint32_t count_cache_legal4(const B& b, const Header& h, int i) {
-  const int n = b.n();
+// legal cells per column of the player to move, four columns per word, from cache word i
+TW_HD uint32_t count_cache_legal4(uint32_t w, const Header& h, int n, int i) {
   if (h.ply == 1u) return bytes4(static_cast<uint32_t>(n - 2)) & column_byte_mask(i, 0, n - 1);
-  const uint32_t w = b.cache_ld(i);
   const uint32_t pegs = w & 0x1F1F1F1Fu, brd = (w >> 5) & 0x03030303u;
   if ((h.ply & 1u) == kRed) return (bytes4(static_cast<uint32_t>(n)) - pegs) & column_byte_mask(i, 1, n - 2);
   return (bytes4(static_cast<uint32_t>(n - 2)) - pegs + brd) & column_byte_mask(i, 0, n - 1);
@@ -564,15 +561,25 @@ TW_HD uint32_t count_cache_legal4(const B& b, const Header& h, int i) {
 template <class B>
 TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, int& out_y) {
   const int n = b.n();
+  constexpr int kMaxWords = 6;  // ceil(24 / 4)
+  const int words = (n + 3) / 4;
+  // all cache words first (independent loads), then the arithmetic
+  uint32_t cw[kMaxWords];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < kMaxWords; ++i) cw[i] = i < words ? b.cache_ld(i) : 0u;
   uint32_t sp = 0;  // byte prefix sums of the selected word
   int si = 0, sk = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < (n + 3) / 4; ++i) {
-    const uint32_t p4 = count_cache_legal4(b, h, i) * 0x01010101u;  // inclusive byte prefix sums
-    if (k >= 0) { sp = p4; si = i; sk = k; }
-    k -= static_cast<int>(p4 >> 24);
+  for (int i = 0; i < kMaxWords; ++i) {
+    if (i < words) {
+      const uint32_t p4 = count_cache_legal4(cw[i], h, n, i) * 0x01010101u;  // inclusive byte prefix sums
+      if (k >= 0) { sp = p4; si = i; sk = k; }
+      k -= static_cast<int>(p4 >> 24);
+    }
   }
   // first byte whose inclusive prefix exceeds sk
   const uint32_t gt = bytes_gt(sp, bytes4(static_cast<uint32_t>(sk)));
