@@ -46,7 +46,13 @@ namespace twixt {
 
 namespace {
 
-constexpr int kPlayoutThreads = 128;  // 4 warps per block
+#ifndef TW_PLAYOUT_THREADS
+#define TW_PLAYOUT_THREADS 128
+#endif
+#ifndef TW_PLAYOUT_MIN_BLOCKS
+#define TW_PLAYOUT_MIN_BLOCKS 1
+#endif
+constexpr int kPlayoutThreads = TW_PLAYOUT_THREADS;  // 4 warps per block
 constexpr int kSmemPlanes = 8;        // P_RED .. P_END
 #ifndef TW_PLAYOUT_STACK_WORDS
 #define TW_PLAYOUT_STACK_WORDS 24
@@ -117,7 +123,7 @@ struct SmemStack {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(kPlayoutThreads) playout_kernel(const PlayoutArgs a) {
+__global__ void __launch_bounds__(kPlayoutThreads, TW_PLAYOUT_MIN_BLOCKS) playout_kernel(const PlayoutArgs a) {
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
   const int n = NT > 0 ? NT : a.n;
