@@ -209,15 +209,17 @@ struct LinkWindow {
   uint32_t w[4][5];
 };
 
-// Is the link with west endpoint (x + ow, wy) and east direction de crossed by
-// any existing link, of either colour (twixtboard.cc:519-527 tests HasLink
-// only)?  ow in {0,-1,-2}.
-TW_HD bool crossing_blocked(const LinkWindow& lw, int ow, int wy, int de) {
-#define TW_X(plane, ox, mask) (lw.w[plane][ow + (ox) + 3] & ((static_cast<uint32_t>(mask) << wy) >> 3))
-#define TW_CROSS_CASE(d, expr) \
-  case d:                      \
+// Would the link from the new peg (x, y) in Compass direction d be crossed by
+// an existing link, of either colour (twixtboard.cc:519-527 tests HasLink
+// only)?  `ly` is the window with every word aligned to the peg's row,
+// (word << 5) >> y, so that row y+oy sits at bit oy+5 and each of the 5..7
+// tests of a direction is one AND with a constant (twixt_crossing.inc).
+TW_HD bool crossing_blocked(const LinkWindow& ly, int d) {
+#define TW_X(plane, c, mask) (ly.w[plane][c] & (mask))
+#define TW_CROSS_CASE(dir, expr) \
+  case dir:                      \
     return (expr) != 0u;
-  switch (de) {
+  switch (d) {
 #include "twixt_crossing.inc"
   }
 #undef TW_CROSS_CASE
@@ -392,7 +394,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
   const uint32_t cand = p.cand;
   if (kAlways || cand) {
     // everything the eight directions may read, fetched with independent loads
-    LinkWindow lw;
+    LinkWindow lw, ly;
     uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
     uint32_t blk[3] = {0u, 0u, 0u};  // new blocked-east bits of columns x, x-1, x-2
 #if defined(__CUDA_ARCH__)
@@ -402,7 +404,10 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (int pl = 0; pl < 4; ++pl) lw.w[pl][c] = b.ld_guard(P_LINK0 + pl, x - 3 + c);
+      for (int pl = 0; pl < 4; ++pl) {
+        lw.w[pl][c] = b.ld_guard(P_LINK0 + pl, x - 3 + c);
+        ly.w[pl][c] = (lw.w[pl][c] << 5) >> y;  // row y+oy at bit oy+5
+      }
       fs[c] = b.ld_guard(P_START, x - 2 + c);
       fe[c] = b.ld_guard(P_END, x - 2 + c);
     }
@@ -417,7 +422,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
       const int ty = is_cand ? y + dy : 0;  // keeps every shift count in range for non-candidates
       // the link named by its west endpoint (x+ow, wy) and east direction de
       const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
-      const bool blocked = crossing_blocked(lw, ow, wy, de);
+      const bool blocked = crossing_blocked(ly, d);
       // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
       // pointing east is ever read (twixtcell.h:82-84) and it always lands on
       // the west endpoint, i.e. in column x, x-1 or x-2 (index -ow)
