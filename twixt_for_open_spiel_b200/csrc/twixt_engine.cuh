@@ -180,7 +180,7 @@ TW_HD int current_player(const Header& h) {
 TW_HD int legal_count(const Header& h, int n) {
   if (h.result != kOpen) return 0;
   if (h.ply == 1u) return n * (n - 2);
-  return h.cnt[h.ply & 1u];
+  return (h.ply & 1u) ? h.cnt[kBlue] : h.cnt[kRed];  // (a run-time index would push the header into local memory)
 }
 
 // Legal cells of the player to move in column x (result must be open).
@@ -457,7 +457,7 @@ TW_HD void finish_move(Header& h, const Placement& p, bool win) {
   if (h.ply == 0u) h.move_one = p.action;
   h.ply += 1u;
   if (win) h.result = p.player == kRed ? kRedWin : kBlueWin;   // twixtboard.cc:194-199
-  else if (h.cnt[1 - p.player] == 0) h.result = kDraw;         // 203-206
+  else if ((p.player == kRed ? h.cnt[kBlue] : h.cnt[kRed]) == 0) h.result = kDraw;  // 203-206
 }
 
 // Board::ApplyAction (twixtboard.cc:457-499) for an action known to be legal,
