@@ -75,10 +75,18 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
   __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
   __device__ __forceinline__ uint32_t* sink() const { return p + (kSmemPlanes * n() + kStackWords + kCacheWords) * 32; }
-  // conditional plane store: a plain branch measured faster here than redirecting the store of the
-  // "false" lanes to the sink word (38.3 vs 39.7 ms per 1 Mi-env launch) -- unlike the stack push below
+  // conditional plane store as ONE predicated st.shared: the compiler turns `if (c) st(...)` into a
+  // BSSY/BRA/BSYNC region (ten of them per move showed up as branch_resolving stalls), and redirecting
+  // the store of the "false" lanes to a sink word measured slower than that
   __device__ __forceinline__ void st_if(bool c, int plane, int col, uint32_t v) {
+#if defined(TW_EXP_BRANCHY_ST)
     if (c) st(plane, col, v);
+#else
+    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p + (plane * n() + col) * 32));
+    asm volatile(
+        "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp st.shared.u32 [%1], %2;\n\t}"
+        :: "r"(static_cast<uint32_t>(c)), "r"(addr), "r"(v) : "memory");
+#endif
   }
   __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
@@ -88,6 +96,15 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
   __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
+  __device__ __forceinline__ void or_blocked_if(bool c, int col, uint32_t bits) {
+#if defined(TW_EXP_BRANCHY_ST)
+    if (c) or_blocked(col, bits);
+#else
+    asm volatile(
+        "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp red.global.or.b32 [%1], %2;\n\t}"
+        :: "r"(static_cast<uint32_t>(c)), "l"(gblk + col), "r"(bits) : "memory");
+#endif
+  }
   // per-column count cache (twixt_engine.cuh, count_cache_*), after the planes and the stack
   static constexpr bool kCountCache = true;
   __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
