@@ -49,6 +49,9 @@ namespace {
 #ifndef TW_PLAYOUT_THREADS
 #define TW_PLAYOUT_THREADS 128
 #endif
+#ifndef TW_EXP_CACHE_IN_SMEM
+#define TW_EXP_CACHE_IN_SMEM 0
+#endif
 #ifndef TW_PLAYOUT_MIN_BLOCKS
 #define TW_PLAYOUT_MIN_BLOCKS 1
 #endif
@@ -105,15 +108,29 @@ struct PlayoutRef {
         :: "r"(static_cast<uint32_t>(c)), "l"(gblk + col), "r"(bits) : "memory");
 #endif
   }
-  // per-column count cache (twixt_engine.cuh, count_cache_*), after the planes and the stack
+  // per-column count cache (twixt_engine.cuh, count_cache_*).  With a compile-time board size every index
+  // into it is static after unrolling, so the six words live in REGISTERS (no load before a selection, no
+  // store->load round trip after a move); the run-time-size instantiation keeps them in shared memory
+  // after the planes and the stack.
   static constexpr bool kCountCache = true;
+  static constexpr bool kCacheInRegs = NT > 0 && !TW_EXP_CACHE_IN_SMEM;
+  uint32_t cw[kCacheWords];
   __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
-  __device__ __forceinline__ uint32_t cache_ld(int i) const { return *cache_word(i); }
-  __device__ __forceinline__ void cache_st(int i, uint32_t v) { *cache_word(i) = v; }
+  __device__ __forceinline__ uint32_t cache_ld(int i) const { return kCacheInRegs ? cw[i] : *cache_word(i); }
+  __device__ __forceinline__ void cache_st(int i, uint32_t v) {
+    if (kCacheInRegs) cw[i] = v;
+    else *cache_word(i) = v;
+  }
   __device__ __forceinline__ void note_peg(int x, int y, int delta) {
     const uint32_t inc = (1u | ((y == 0 || y == n() - 1) ? 32u : 0u)) << (8 * (x & 3));
-    uint32_t* w = cache_word(x >> 2);
-    *w = delta > 0 ? *w + inc : *w - inc;
+    const uint32_t signed_inc = delta > 0 ? inc : 0u - inc;
+    if (kCacheInRegs) {
+#pragma unroll
+      for (int i = 0; i < kCacheWords; ++i) cw[i] += (i == (x >> 2)) ? signed_inc : 0u;
+    } else {
+      uint32_t* w = cache_word(x >> 2);
+      *w += signed_inc;
+    }
   }
 };
 
@@ -155,7 +172,12 @@ __global__ void __launch_bounds__(kPlayoutThreads, TW_PLAYOUT_MIN_BLOCKS) playou
   uint32_t* grec = nullptr;
   Header h;
   h.ply = 0; h.result = kDraw; h.swapped = 0; h.move_one = kNoMove; h.cnt[0] = h.cnt[1] = 0;
-  PlayoutRef<NT> b{mine, nullptr, n};
+  PlayoutRef<NT> b;
+  b.p = mine;
+  b.gblk = nullptr;
+  b.n_rt = n;
+#pragma unroll
+  for (int i = 0; i < kCacheWords; ++i) b.cw[i] = 0u;
   SmemStack stk{mine + kSmemPlanes * n * 32, 0, false, b.sink()};
   uint32_t s_lo = 0, s_hi = 0;
   // Random words: block `rq` (moves 4rq..4rq+3) in ra[], block rq+1 in rb[].  Lanes of a warp are at
