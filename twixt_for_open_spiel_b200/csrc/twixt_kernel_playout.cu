@@ -156,8 +156,15 @@ struct SmemStack {
   __device__ __forceinline__ uint32_t pop() { return base[(--sp) * 32]; }
 };
 
+// resident blocks per SM the register allocation should allow: what shared memory allows for that size
+__host__ __device__ constexpr int playout_min_blocks(int nt) {
+  return nt == 0 ? TW_PLAYOUT_MIN_BLOCKS : (227 * 1024) / (kPlayoutThreads * playout_words(nt) * 4 + 1024) > 4
+                                               ? 4
+                                               : (227 * 1024) / (kPlayoutThreads * playout_words(nt) * 4 + 1024);
+}
+
 template <int NT>
-__global__ void __launch_bounds__(kPlayoutThreads, TW_PLAYOUT_MIN_BLOCKS) playout_kernel(const PlayoutArgs a) {
+__global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playout_kernel(const PlayoutArgs a) {
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
   const int n = NT > 0 ? NT : a.n;
