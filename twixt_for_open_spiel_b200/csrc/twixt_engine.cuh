@@ -155,10 +155,12 @@ TW_HD uint32_t inner_rows(int n) { return ((1u << n) - 1u) & ~1u & ~(1u << (n - 
 
 // Cells `player` may ever play on in column x: red everything in columns
 // 1..n-2, blue rows 1..n-2 of every column (InitializeLegalActions,
-// twixtboard.cc:252-276; corners are off-board, 625-631).
+// twixtboard.cc:252-276; corners are off-board, 625-631).  Written with selects
+// only: these helpers sit in the hottest loops and a branch per call costs more
+// than computing both sides.
 TW_HD uint32_t playable_word(int n, int player, int x) {
-  if (player == kRed) return (x >= 1 && x <= n - 2) ? full_rows(n) : 0u;
-  return inner_rows(n);
+  const uint32_t red = (x >= 1 && x <= n - 2) ? full_rows(n) : 0u;
+  return player == kRed ? red : inner_rows(n);
 }
 
 // The initial record of an env (Board::Board, twixtboard.cc:168-174).
@@ -181,18 +183,18 @@ TW_HD int current_player(const Header& h) {
 // one -- the occupied first-move cell stays in it as the swap offer
 // (twixtboard.cc:485-488) -- from ply 2 on both lists are "playable and empty".
 TW_HD int legal_count(const Header& h, int n) {
-  if (h.result != kOpen) return 0;
-  if (h.ply == 1u) return n * (n - 2);
-  return (h.ply & 1u) ? h.cnt[kBlue] : h.cnt[kRed];  // (a run-time index would push the header into local memory)
+  const int by_count = (h.ply & 1u) ? h.cnt[kBlue] : h.cnt[kRed];  // (a run-time index would push the header into local memory)
+  const int open_count = h.ply == 1u ? n * (n - 2) : by_count;
+  return h.result != kOpen ? 0 : open_count;
 }
 
 // Legal cells of the player to move in column x (result must be open).
 template <class B>
 TW_HD uint32_t legal_word(const B& b, const Header& h, int x) {
-  int player = static_cast<int>(h.ply & 1u);
-  uint32_t play = playable_word(b.n(), player, x);
-  if (h.ply == 1u) return play;
-  return play & ~(b.ld_pegs(P_RED, x) | b.ld_pegs(P_BLUE, x));
+  const int player = static_cast<int>(h.ply & 1u);
+  const uint32_t play = playable_word(b.n(), player, x);
+  const uint32_t occ = b.ld_pegs(P_RED, x) | b.ld_pegs(P_BLUE, x);
+  return h.ply == 1u ? play : (play & ~occ);
 }
 
 template <class B>
@@ -556,12 +558,15 @@ TW_HD void count_cache_build(B& b) {
   }
 }
 
-// legal cells per column of the player to move, four columns per word, from cache word i
+// legal cells per column of the player to move, four columns per word, from cache word i (selects only)
 TW_HD uint32_t count_cache_legal4(uint32_t w, const Header& h, int n, int i) {
-  if (h.ply == 1u) return bytes4(static_cast<uint32_t>(n - 2)) & column_byte_mask(i, 0, n - 1);
   const uint32_t pegs = w & 0x1F1F1F1Fu, brd = (w >> 5) & 0x03030303u;
-  if ((h.ply & 1u) == kRed) return (bytes4(static_cast<uint32_t>(n)) - pegs) & column_byte_mask(i, 1, n - 2);
-  return (bytes4(static_cast<uint32_t>(n - 2)) - pegs + brd) & column_byte_mask(i, 0, n - 1);
+  const uint32_t every = column_byte_mask(i, 0, n - 1);
+  const uint32_t first4 = bytes4(static_cast<uint32_t>(n - 2)) & every;                 // ply 1: the full initial list
+  const uint32_t red4 = (bytes4(static_cast<uint32_t>(n)) - pegs) & column_byte_mask(i, 1, n - 2);
+  const uint32_t blue4 = (bytes4(static_cast<uint32_t>(n - 2)) - pegs + brd) & every;
+  const uint32_t by_player = (h.ply & 1u) == kRed ? red4 : blue4;
+  return h.ply == 1u ? first4 : by_player;
 }
 
 template <class B>
