@@ -111,8 +111,11 @@ struct RecordRef {
   TW_HD uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // the blocked plane is write-only for the rules (only ObservationTensor reads it)
   TW_HD void or_blocked(int col, uint32_t bits) { st(P_BLOCKED, col, ld(P_BLOCKED, col) | bits); }
-  TW_HD void or_blocked_if(bool c, int col, uint32_t bits) {
-    if (c) or_blocked(col, bits);
+  // new blocked-east bits of the columns x, x-1, x-2 (blk[i] for column x-i; all zero most of the time)
+  TW_HD void or_blocked3(int x, const uint32_t blk[3]) {
+    if (blk[0]) or_blocked(x, blk[0]);
+    if (blk[1]) or_blocked(x - 1, blk[1]);
+    if (blk[2]) or_blocked(x - 2, blk[2]);
   }
   // no per-column count cache on a plain record (see count_cache_* below)
   static constexpr bool kCountCache = false;
@@ -442,9 +445,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
       to_end |= make && !ts && te;           // 541-543
       neutral |= make && !ts && !te;         // 544-546
     }
-    b.or_blocked_if(blk[0] != 0u, x, blk[0]);
-    b.or_blocked_if(blk[1] != 0u, x - 1, blk[1]);
-    b.or_blocked_if(blk[2] != 0u, x - 2, blk[2]);
+    b.or_blocked3(x, blk);
     // the new peg's own flag words are fs[2] / fe[2]
     b.st_if(to_start, P_START, x, fs[2] | bit);
     b.st_if(to_end, P_END, x, fe[2] | bit);

@@ -99,14 +99,15 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
   __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
-  __device__ __forceinline__ void or_blocked_if(bool c, int col, uint32_t bits) {
-#if defined(TW_EXP_BRANCHY_ST)
-    if (c) or_blocked(col, bits);
-#else
-    asm volatile(
-        "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp red.global.or.b32 [%1], %2;\n\t}"
-        :: "r"(static_cast<uint32_t>(c)), "l"(gblk + col), "r"(bits) : "memory");
-#endif
+  // One branch around all three columns: inside it the REDs are unconditional (OR-ing zero bits is
+  // harmless, and a column left of the board only ever has zero bits: its address is clamped), because
+  // ptxas turns every conditional RED into its own BSSY/BRA/BSYNC region.
+  __device__ __forceinline__ void or_blocked3(int x, const uint32_t blk[3]) {
+    if (blk[0] | blk[1] | blk[2]) {
+      atomicOr(gblk + x, blk[0]);
+      atomicOr(gblk + max(x - 1, 0), blk[1]);
+      atomicOr(gblk + max(x - 2, 0), blk[2]);
+    }
   }
   // per-column count cache (twixt_engine.cuh, count_cache_*).  With a compile-time board size every index
   // into it is static after unrolling, so the six words live in REGISTERS (no load before a selection, no
