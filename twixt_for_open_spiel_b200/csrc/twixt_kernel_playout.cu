@@ -164,7 +164,8 @@ __host__ __device__ constexpr int playout_min_blocks(int nt) {
                                                : (227 * 1024) / (kPlayoutThreads * playout_words(nt) * 4 + 1024);
 }
 
-template <int NT>
+// kTrace: write the action trace (only parity tests ask for it; the branch is compiled out otherwise)
+template <int NT, bool kTrace>
 __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playout_kernel(const PlayoutArgs a) {
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     }
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
-      if (a.out_actions != nullptr && step < a.trace_plies)
+      if (kTrace && step < a.trace_plies)
         a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(sx * n + sy);
       const Placement pl = begin_move(b, h, sx, sy);
       // choose the following move now (speculatively: unused if this move ends the game); it only reads the
@@ -369,29 +370,41 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
 
 int g_num_sms = 0;
 
-template <int NT>
+template <int NT, bool kTrace>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(a.n) * sizeof(uint32_t);
   // persistent grid: as many blocks as fit on the device at once (or fewer for small ranges)
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, playout_kernel<NT>, kPlayoutThreads, smem);
+  cudaError_t e =
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, playout_kernel<NT, kTrace>, kPlayoutThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
   const int64_t resident = static_cast<int64_t>(g_num_sms > 0 ? g_num_sms : 148) * per_sm;
   if (blocks > resident) blocks = resident;
-  playout_kernel<NT><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
+  playout_kernel<NT, kTrace><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
   return cudaGetLastError();
+}
+
+template <int NT, bool kTrace>
+cudaError_t setup_one(int n_for_size) {
+  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(playout_kernel<NT, kTrace>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
 }
 
 template <int NT>
 cudaError_t setup_nt(int n_for_size) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(playout_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = setup_one<NT, false>(n_for_size);
+  return e != cudaSuccess ? e : setup_one<NT, true>(n_for_size);
+}
+
+template <int NT>
+cudaError_t launch_traced_or_not(const PlayoutArgs& a, cudaStream_t s) {
+  return a.out_actions != nullptr ? launch_nt<NT, true>(a, s) : launch_nt<NT, false>(a, s);
 }
 
 }  // namespace
@@ -410,10 +423,10 @@ cudaError_t playout_setup() {
 cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s) {
   if (a.count <= 0) return cudaSuccess;
   switch (a.n) {
-    case 8: return launch_nt<8>(a, s);
-    case 12: return launch_nt<12>(a, s);
-    case 24: return launch_nt<24>(a, s);
-    default: return launch_nt<0>(a, s);
+    case 8: return launch_traced_or_not<8>(a, s);
+    case 12: return launch_traced_or_not<12>(a, s);
+    case 24: return launch_traced_or_not<24>(a, s);
+    default: return launch_traced_or_not<0>(a, s);
   }
 }
 
