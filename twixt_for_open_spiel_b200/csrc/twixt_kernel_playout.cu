@@ -232,7 +232,12 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     __pipeline_wait_prior(0);
     unpack_header(stk.base[0], stk.base[32], stk.base[64], stk.base[96], h);
     b.gblk = grec + kHeaderWords + P_BLOCKED * n;
-    count_cache_build(b);
+    if (h.ply == 0u) {  // a fresh game has no pegs: skip the 2n popcounts
+#pragma unroll
+      for (int i = 0; i < kCacheWords; ++i) b.cache_st(i, 0u);
+    } else {
+      count_cache_build(b);
+    }
     const uint64_t stream = a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx);
     s_lo = static_cast<uint32_t>(stream);
     s_hi = static_cast<uint32_t>(stream >> 32);
