@@ -428,29 +428,46 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
+    uint32_t made[5] = {0u, 0u, 0u, 0u, 0u};  // newly linked cells of columns x-2 .. x+2, as row masks
     for (int d = 0; d < 8; ++d) {
       // straight-line per direction (no branch around the test: it is a dozen
       // register-only instructions, cheaper than a divergent branch)
       const int dx = dir_dx(d), dy = dir_dy(d);
       const bool is_cand = (cand >> d) & 1u;
-      const int ty = is_cand ? y + dy : 0;  // keeps every shift count in range for non-candidates
-      // the link named by its west endpoint (x+ow, wy) and east direction de
-      const int ow = d < 4 ? 0 : dx, wy = d < 4 ? y : ty, de = d & 3;
+      // the target cell's row as a mask; a shifted-out bit only happens for non-candidates
+      const uint32_t tbit = dy > 0 ? (bit << dy) : (bit >> (-dy));
+      // the link named by its west endpoint (column x+ow, row mask wbit) and east direction de
+      const int ow = d < 4 ? 0 : dx, de = d & 3;
+      const uint32_t wbit = d < 4 ? bit : tbit;
       const bool blocked = crossing_blocked(ly, d);
       // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
       // pointing east is ever read (twixtcell.h:82-84) and it always lands on
       // the west endpoint, i.e. in column x, x-1 or x-2 (index -ow)
-      blk[-ow] |= (is_cand && blocked) ? (1u << wy) : 0u;
+      blk[-ow] |= (is_cand && blocked) ? wbit : 0u;
       const bool make = is_cand && !blocked;
       // each direction owns a distinct (plane, column) word, and links made
       // earlier in this move never cross later ones (they share the new peg)
-      b.st_if(make, P_LINK0 + de, x + ow, lw.w[de][ow + 3] | (1u << wy));
-      const bool ts = (fs[dx + 2] >> ty) & 1u, te = (fe[dx + 2] >> ty) & 1u;
-      new_links |= make;
-      to_start |= make && ts;                // twixtboard.cc:538-540
-      to_end |= make && !ts && te;           // 541-543
-      neutral |= make && !ts && !te;         // 544-546
+      b.st_if(make, P_LINK0 + de, x + ow, lw.w[de][ow + 3] | wbit);
+      made[dx + 2] |= make ? tbit : 0u;
     }
+    // what the new links reach, column-parallel: a start-flagged peg gives the start flag, otherwise an
+    // end-flagged one the end flag, otherwise the link is neutral (twixtboard.cc:538-546)
+    uint32_t any = 0u, hit_s = 0u, hit_e = 0u, hit_n = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 5; ++c) {
+      if (c == 2) continue;
+      const uint32_t rest = made[c] & ~fs[c];
+      any |= made[c];
+      hit_s |= made[c] & fs[c];
+      hit_e |= rest & fe[c];
+      hit_n |= rest & ~fe[c];
+    }
+    new_links = any != 0u;
+    to_start |= hit_s != 0u;
+    to_end |= hit_e != 0u;
+    neutral = hit_n != 0u;
     b.or_blocked3(x, blk);
     // the new peg's own flag words are fs[2] / fe[2]
     b.st_if(to_start, P_START, x, fs[2] | bit);
