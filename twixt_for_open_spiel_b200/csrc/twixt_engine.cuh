@@ -348,7 +348,9 @@ enum : uint32_t { kFloodStart = 1u, kFloodEnd = 2u };
 struct Placement {
   int x, y;        // where the peg went (differs from the action's cell after a swap)
   int player;
-  uint32_t cand;   // Compass-ordered 8-bit mask of own-colour knight neighbours
+  // own-colour pegs a knight's move away, as row masks of the columns x-2, x-1, x+1, x+2
+  // (index = dx + 2; entry 2 unused): the link candidates
+  uint32_t cand[5];
   uint32_t action; // the action as played
 };
 
@@ -379,12 +381,14 @@ TW_HD Placement begin_move(B& b, Header& h, int x, int y) {
   b.note_peg(x, y, +1);
   h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
   h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
-  // own-colour pegs a knight's move away, as a Compass-ordered 8-bit mask
-  const uint32_t e1 = b.ld_pegs_guard(own, x + 1), e2 = b.ld_pegs_guard(own, x + 2);
-  const uint32_t w1 = b.ld_pegs_guard(own, x - 1), w2 = b.ld_pegs_guard(own, x - 2);
-  p.cand = ((e1 >> (y + 2)) & 1u) | (((e2 >> (y + 1)) & 1u) << 1) | ((((e2 << 1) >> y) & 1u) << 2) |
-           ((((e1 << 2) >> y) & 1u) << 3) | ((((w1 << 2) >> y) & 1u) << 4) | ((((w2 << 1) >> y) & 1u) << 5) |
-           (((w2 >> (y + 1)) & 1u) << 6) | (((w1 >> (y + 2)) & 1u) << 7);
+  // own-colour pegs a knight's move away: rows y+-2 of the columns x+-1, rows y+-1 of the columns x+-2
+  const uint32_t bit = 1u << y;
+  const uint32_t rows2 = (bit << 2) | (bit >> 2), rows1 = (bit << 1) | (bit >> 1);
+  p.cand[0] = b.ld_pegs_guard(own, x - 2) & rows1;
+  p.cand[1] = b.ld_pegs_guard(own, x - 1) & rows2;
+  p.cand[2] = 0u;
+  p.cand[3] = b.ld_pegs_guard(own, x + 1) & rows2;
+  p.cand[4] = b.ld_pegs_guard(own, x + 2) & rows1;
   return p;
 }
 
@@ -405,8 +409,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
   bool to_start = p.player == kRed ? (y == 0) : (x == 0);
   bool to_end = p.player == kRed ? (y == n - 1) : (x == n - 1);
   bool neutral = false, new_links = false;
-  const uint32_t cand = p.cand;
-  if (kAlways || cand) {
+  if (kAlways || (p.cand[0] | p.cand[1] | p.cand[3] | p.cand[4])) {
     // everything the eight directions may read, fetched with independent loads
     LinkWindow lw, ly;
     uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
@@ -433,9 +436,9 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
       // straight-line per direction (no branch around the test: it is a dozen
       // register-only instructions, cheaper than a divergent branch)
       const int dx = dir_dx(d), dy = dir_dy(d);
-      const bool is_cand = (cand >> d) & 1u;
       // the target cell's row as a mask; a shifted-out bit only happens for non-candidates
       const uint32_t tbit = dy > 0 ? (bit << dy) : (bit >> (-dy));
+      const bool is_cand = (p.cand[dx + 2] & tbit) != 0u;
       // the link named by its west endpoint (column x+ow, row mask wbit) and east direction de
       const int ow = d < 4 ? 0 : dx, de = d & 3;
       const uint32_t wbit = d < 4 ? bit : tbit;
