@@ -158,7 +158,7 @@ int he_playout_cached(uint32_t* rec, int n, uint64_t seed, uint64_t stream, int 
       select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
       const bool win = link_move<true>(b, pl, pend);
       finish_move(h, pl, win);
-      origin = static_cast<uint32_t>((pl.x << 8) | pl.y);
+      origin = flood_entry(pl.x, 1u << pl.y);
       ++step;
       playing = h.result == kOpen && step < max_plies;
       sx = nx;

@@ -122,21 +122,31 @@ struct RecordRef {
   TW_HD void note_peg(int, int, int) {}
 };
 
-// Flood-fill work stack kept in a thread-local array (apply kernel, host tests).
+// Flood-fill work stack.  An entry names up to 24 cells of ONE column:
+// (column << 24) | row mask -- the flood discovers unflagged neighbours column
+// by column, so a visit pushes at most four entries instead of eight cells.
+TW_HD uint32_t flood_entry(int column, uint32_t row_mask) { return (static_cast<uint32_t>(column) << 24) | row_mask; }
+
+// ... kept in a thread-local array (apply kernel, host tests).
 template <int kCap>
 struct LocalStack {
-  uint16_t v[kCap];
+  uint32_t v[kCap];
   int sp = 0;
   bool overflow = false;
   TW_HD bool empty() const { return sp == 0; }
-  TW_HD void push(uint32_t c) {
-    if (sp < kCap) v[sp++] = static_cast<uint16_t>(c);
+  TW_HD void push(uint32_t e) {
+    if (sp < kCap) v[sp++] = e;
     else overflow = true;
   }
-  TW_HD void push_if(bool c, uint32_t cell) {
-    if (c) push(cell);
+  TW_HD void push_if(bool c, uint32_t e) {
+    if (c) push(e);
   }
-  TW_HD uint32_t pop() { return v[--sp]; }
+  TW_HD uint32_t top() const { return v[sp - 1]; }
+  // after one cell of the top entry was taken: keep the entry with the remaining rows, or drop it
+  TW_HD void retop(bool keep, uint32_t e) {
+    if (keep) v[sp - 1] = e;
+    else --sp;
+  }
 };
 
 template <class B>
@@ -266,9 +276,12 @@ TW_HD uint32_t links_of(const B& b, int x, int y) {
 // per-direction formulation was 40 % more instructions.)
 template <class B, class Stack>
 TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
-  const uint32_t c = stk.pop();
-  const int cx = static_cast<int>(c >> 8), cy = static_cast<int>(c & 255u);
+  // take the lowest cell of the top entry
+  const uint32_t e = stk.top();
+  const uint32_t rows = e & 0x00FFFFFFu;
+  const int cx = static_cast<int>(e >> 24), cy = tw_ctz(rows);
   const uint32_t bit = 1u << cy;
+  stk.retop((rows & (rows - 1u)) != 0u, e & ~bit);
   // links stored at this cell (it is their west endpoint): NNE, ENE, ESE, SSE
   const uint32_t own0 = b.ld(P_LINK0 + 0, cx) & bit, own1 = b.ld(P_LINK0 + 1, cx) & bit;
   const uint32_t own2 = b.ld(P_LINK0 + 2, cx) & bit, own3 = b.ld(P_LINK0 + 3, cx) & bit;
@@ -286,15 +299,10 @@ TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
   b.st_if(n_e2 != 0u, flag_plane, cx + 2, f_e2 | n_e2);
   b.st_if(n_w1 != 0u, flag_plane, cx - 1, f_w1 | n_w1);
   b.st_if(n_w2 != 0u, flag_plane, cx - 2, f_w2 | n_w2);
-  // cells are encoded (x << 8) | y, so a neighbour is c plus a constant
-  stk.push_if((n_e1 & (bit << 2)) != 0u, c + 0x100u + 2u);
-  stk.push_if((n_e1 & (bit >> 2)) != 0u, c + 0x100u - 2u);
-  stk.push_if((n_e2 & (bit << 1)) != 0u, c + 0x200u + 1u);
-  stk.push_if((n_e2 & (bit >> 1)) != 0u, c + 0x200u - 1u);
-  stk.push_if((n_w1 & (bit >> 2)) != 0u, c - 0x100u - 2u);
-  stk.push_if((n_w1 & (bit << 2)) != 0u, c - 0x100u + 2u);
-  stk.push_if((n_w2 & (bit >> 1)) != 0u, c - 0x200u - 1u);
-  stk.push_if((n_w2 & (bit << 1)) != 0u, c - 0x200u + 1u);
+  stk.push_if(n_e1 != 0u, flood_entry(cx + 1, n_e1));
+  stk.push_if(n_e2 != 0u, flood_entry(cx + 2, n_e2));
+  stk.push_if(n_w1 != 0u, flood_entry(cx - 1, n_w1));
+  stk.push_if(n_w2 != 0u, flood_entry(cx - 2, n_w2));
 }
 
 // If the stack overflowed, the dropped cells are recovered by closing the
@@ -331,7 +339,7 @@ TW_HD_NOINLINE void flood_closure(B& b, int own_plane, int flag_plane) {
 template <int kStack, class B>
 TW_HD_NOINLINE void flood_flag(B& b, int own_plane, int flag_plane, int x, int y) {
   LocalStack<kStack> stk;
-  stk.push(static_cast<uint32_t>((x << 8) | y));
+  stk.push(flood_entry(x, 1u << y));
   while (!stk.empty()) flood_visit(b, flag_plane, stk);
   if (stk.overflow) flood_closure(b, own_plane, flag_plane);
 }

@@ -154,7 +154,12 @@ struct SmemStack {
     sp += doit ? 1 : 0;
     overflow |= c && !room;
   }
-  __device__ __forceinline__ uint32_t pop() { return base[(--sp) * 32]; }
+  __device__ __forceinline__ uint32_t top() const { return base[(sp - 1) * 32]; }
+  // after one cell of the top entry was taken: keep the entry with the remaining rows, or drop it
+  __device__ __forceinline__ void retop(bool keep, uint32_t e) {
+    if (keep) base[(sp - 1) * 32] = e;
+    sp -= keep ? 0 : 1;
+  }
 };
 
 // resident blocks per SM the register allocation should allow: what shared memory allows for that size
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
       const bool win = link_move<true>(b, pl, pend);
       finish_move(h, pl, win);
-      origin = static_cast<uint32_t>((pl.x << 8) | pl.y);
+      origin = flood_entry(pl.x, 1u << pl.y);
       ++step;
       playing = h.result == kOpen && step < a.max_plies;
       sx = nx;
