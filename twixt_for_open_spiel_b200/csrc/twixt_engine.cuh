@@ -439,27 +439,40 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    uint32_t made[5] = {0u, 0u, 0u, 0u, 0u};  // newly linked cells of columns x-2 .. x+2, as row masks
+    // crossed[c]: cells of column x-2+c the link to which would be crossed, as row masks
+    uint32_t crossed[5] = {0u, 0u, 0u, 0u, 0u};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int d = 0; d < 8; ++d) {
-      // straight-line per direction (no branch around the test: it is a dozen
-      // register-only instructions, cheaper than a divergent branch)
       const int dx = dir_dx(d), dy = dir_dy(d);
-      // the target cell's row as a mask; a shifted-out bit only happens for non-candidates
+      const uint32_t tbit = dy > 0 ? (bit << dy) : (bit >> (-dy));  // the target cell's row
+      crossed[dx + 2] |= crossing_blocked(ly, d) ? tbit : 0u;
+    }
+    // made[c] / blocked candidates per column, column-parallel
+    uint32_t made[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 5; ++c) made[c] = p.cand[c] & ~crossed[c];
+    // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit pointing east is ever read
+    // (twixtcell.h:82-84) and it always lands on the WEST endpoint of the refused link: the new peg
+    // itself for the four east directions, the target for the west ones (columns x-1, x-2)
+    blk[0] = ((p.cand[3] & crossed[3]) | (p.cand[4] & crossed[4])) ? bit : 0u;
+    blk[1] = p.cand[1] & crossed[1];
+    blk[2] = p.cand[0] & crossed[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int d = 0; d < 8; ++d) {
+      const int dx = dir_dx(d), dy = dir_dy(d);
       const uint32_t tbit = dy > 0 ? (bit << dy) : (bit >> (-dy));
-      const bool is_cand = (p.cand[dx + 2] & tbit) != 0u;
-      // the link named by its west endpoint (column x+ow, row mask wbit) and east direction de
+      // the link named by its west endpoint (column x+ow, row mask wbit) and east direction de; each
+      // direction owns a distinct (plane, column) word, and links made earlier in this move never cross
+      // later ones (they share the new peg)
       const int ow = d < 4 ? 0 : dx, de = d & 3;
       const uint32_t wbit = d < 4 ? bit : tbit;
-      const bool blocked = crossing_blocked(ly, d);
-      // SetBlockedNeighbor on both ends (twixtboard.cc:550-551); only the bit
-      // pointing east is ever read (twixtcell.h:82-84) and it always lands on
-      // the west endpoint, i.e. in column x, x-1 or x-2 (index -ow)
-      blk[-ow] |= (is_cand && blocked) ? wbit : 0u;
-      const bool make = is_cand && !blocked;
-      // each direction owns a distinct (plane, column) word, and links made
-      // earlier in this move never cross later ones (they share the new peg)
-      b.st_if(make, P_LINK0 + de, x + ow, lw.w[de][ow + 3] | wbit);
-      made[dx + 2] |= make ? tbit : 0u;
+      b.st_if((made[dx + 2] & tbit) != 0u, P_LINK0 + de, x + ow, lw.w[de][ow + 3] | wbit);
     }
     // what the new links reach, column-parallel: a start-flagged peg gives the start flag, otherwise an
     // end-flagged one the end flag, otherwise the link is neutral (twixtboard.cc:538-546)
