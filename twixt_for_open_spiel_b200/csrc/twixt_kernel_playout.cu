@@ -52,6 +52,9 @@ namespace {
 #ifndef TW_EXP_CACHE_IN_SMEM
 #define TW_EXP_CACHE_IN_SMEM 0
 #endif
+#ifndef TW_EXP_LINK_ALWAYS
+#define TW_EXP_LINK_ALWAYS true
+#endif
 #ifndef TW_PLAYOUT_MIN_BLOCKS
 #define TW_PLAYOUT_MIN_BLOCKS 1
 #endif
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       const int ln = legal_count(hn, n);
       int nx, ny;
       select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
-      const bool win = link_move<true>(b, pl, pend);
+      const bool win = link_move<TW_EXP_LINK_ALWAYS>(b, pl, pend);
       finish_move(h, pl, win);
       origin = flood_entry(pl.x, 1u << pl.y);
       ++step;
