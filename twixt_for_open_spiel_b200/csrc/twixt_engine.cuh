@@ -606,15 +606,31 @@ TW_HD void count_cache_build(B& b) {
   }
 }
 
-// legal cells per column of the player to move, four columns per word, from cache word i (selects only)
-TW_HD uint32_t count_cache_legal4(uint32_t w, const Header& h, int n, int i) {
-  const uint32_t pegs = w & 0x1F1F1F1Fu, brd = (w >> 5) & 0x03030303u;
-  const uint32_t every = column_byte_mask(i, 0, n - 1);
-  const uint32_t first4 = bytes4(static_cast<uint32_t>(n - 2)) & every;                 // ply 1: the full initial list
-  const uint32_t red4 = (bytes4(static_cast<uint32_t>(n)) - pegs) & column_byte_mask(i, 1, n - 2);
-  const uint32_t blue4 = (bytes4(static_cast<uint32_t>(n - 2)) - pegs + brd) & every;
-  const uint32_t by_player = (h.ply & 1u) == kRed ? red4 : blue4;
-  return h.ply == 1u ? first4 : by_player;
+// Legal cells per column of the player to move, four columns per word, from cache word i.  What depends on
+// the position's mode (ply 1 / red to move / blue to move) is folded into three constants chosen once per
+// selection, so each word costs five instructions:
+//   count4 = (base4 - (w & pegm) + ((w >> 5) & brdm)) & columns_i
+//   ply 1: base4 = n-2, pegm = brdm = 0     (the full initial list, every column)
+//   red  : base4 = n,   pegm = pegs, brdm = 0   (columns 1..n-2)
+//   blue : base4 = n-2, pegm = pegs, brdm = border pegs (every column)
+struct CountMode {
+  uint32_t base4, pegm, brdm;
+  bool red;
+};
+TW_HD CountMode count_mode(const Header& h, int n) {
+  const bool first = h.ply == 1u;
+  const bool red = !first && (h.ply & 1u) == kRed;
+  CountMode m;
+  m.base4 = bytes4(static_cast<uint32_t>(red ? n : n - 2));
+  m.pegm = first ? 0u : 0x1F1F1F1Fu;
+  m.brdm = (first || red) ? 0u : 0x03030303u;
+  m.red = red;
+  return m;
+}
+TW_HD uint32_t count_cache_legal4(uint32_t w, const CountMode& m, int n, int i) {
+  const uint32_t inner = column_byte_mask(i, 1, n - 2), every = column_byte_mask(i, 0, n - 1);
+  const uint32_t columns = inner == every ? every : (m.red ? inner : every);  // differs in the two edge words only
+  return (m.base4 - (w & m.pegm) + ((w >> 5) & m.brdm)) & columns;
 }
 
 template <class B>
@@ -628,6 +644,7 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
 #pragma unroll
 #endif
   for (int i = 0; i < kMaxWords; ++i) cw[i] = i < words ? b.cache_ld(i) : 0u;
+  const CountMode mode = count_mode(h, n);
   uint32_t sp = 0;  // byte prefix sums of the selected word
   int si = 0, sk = 0;
 #if defined(__CUDA_ARCH__)
@@ -635,7 +652,7 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
 #endif
   for (int i = 0; i < kMaxWords; ++i) {
     if (i < words) {
-      const uint32_t p4 = count_cache_legal4(cw[i], h, n, i) * 0x01010101u;  // inclusive byte prefix sums
+      const uint32_t p4 = count_cache_legal4(cw[i], mode, n, i) * 0x01010101u;  // inclusive byte prefix sums
       if (k >= 0) { sp = p4; si = i; sk = k; }
       k -= static_cast<int>(p4 >> 24);
     }
