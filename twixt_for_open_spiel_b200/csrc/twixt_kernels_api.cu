@@ -93,18 +93,44 @@ __device__ __forceinline__ uint32_t legal_word_of(const LegalInputs& in, int n, 
 // same load whatever the board size (a chunk spans at most two column words,
 // fetched from their lanes by shuffle).  popc + warp prefix sum give every
 // chunk its offset in the ascending list; each lane expands its chunk into a
-// shared-memory row, then the warp streams the row out with coalesced vector
-// stores.
+// shared-memory row with a fixed, branch-free run of predicated stores (one
+// bit test, one store and one pointer bump per cell: no loop, no divergence
+// between lanes with different populations), then the warp streams the row
+// out with coalesced 16-byte stores.
+constexpr int kMaxChunkBits = (TWIXT_MAX_BOARD_SIZE * TWIXT_MAX_BOARD_SIZE + 31) / 32;
+static_assert(kMaxChunkBits < 32, "chunk populations must fit the 5-ballot prefix sum");
+
+// 16 bytes of output (kPerVec = 16 / sizeof(T) actions) from the uint16 staging row, vector index v
 template <typename T>
-__global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
+__device__ __forceinline__ uint4 widen_actions(const uint16_t* row, int v);
+template <>
+__device__ __forceinline__ uint4 widen_actions<uint16_t>(const uint16_t* row, int v) {
+  return reinterpret_cast<const uint4*>(row)[v];
+}
+template <>
+__device__ __forceinline__ uint4 widen_actions<int32_t>(const uint16_t* row, int v) {
+  const uint2 p = reinterpret_cast<const uint2*>(row)[v];
+  return make_uint4(p.x & 0xFFFFu, p.x >> 16, p.y & 0xFFFFu, p.y >> 16);
+}
+template <>
+__device__ __forceinline__ uint4 widen_actions<int64_t>(const uint16_t* row, int v) {
+  const uint32_t p = reinterpret_cast<const uint32_t*>(row)[v];
+  return make_uint4(p & 0xFFFFu, 0u, p >> 16, 0u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLegalWarps * 32, 6) legal_actions_kernel(
     const uint32_t* __restrict__ records, int64_t count, int n, int rw, T* __restrict__ out_actions, int64_t stride,
     int32_t* __restrict__ out_counts) {
-  __shared__ __align__(16) T rows[kLegalWarps][TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2)];
+  constexpr int kPerVec = 16 / static_cast<int>(sizeof(T));
+  // the row is staged as uint16 whatever T is (actions < 576): a quarter of the shared-memory traffic of an
+  // int64 row; the copy-out widens kPerVec entries into each 16-byte store
+  __shared__ __align__(16) uint16_t rows[kLegalWarps][TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLegalWarps;
   int64_t env = blockIdx.x * static_cast<int64_t>(kLegalWarps) + warp;
   if (env >= count) return;  // whole warp leaves together
-  T* row = rows[warp];
+  uint16_t* row = rows[warp];
   // this lane's chunk of the flat cell string: cells [first, first + chunk_bits)
   const int cells = n * n;
   const int chunk_bits = (cells + 31) >> 5;
@@ -112,49 +138,56 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_actions_kernel(
   const int x0 = min(first / n, n - 1), y0 = first - (first / n) * n;
   const int x1 = min(x0 + 1, n - 1);
   const uint32_t chunk_mask = first >= cells ? 0u : ((1u << min(chunk_bits, cells - first)) - 1u);
-  LegalInputs cur = legal_fetch(records + env * rw, n, lane);
+  const int64_t rec_step = nwarps * rw;
+  const uint32_t* rec = records + env * rw;
+  T* dst = out_actions != nullptr ? out_actions + env * stride : nullptr;
+  const int64_t dst_step = nwarps * stride;
+  // rows start 16-byte aligned for every env iff the base is and the stride is a whole number of vectors
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(out_actions) & 15u) == 0 && stride % kPerVec == 0;
+  LegalInputs cur = legal_fetch(rec, n, lane);
   for (; env < count; env += nwarps) {
-    const int64_t next = env + nwarps;
+    rec += rec_step;
     LegalInputs nxt = cur;
-    if (next < count) nxt = legal_fetch(records + next * rw, n, lane);
+    if (env + nwarps < count) nxt = legal_fetch(rec, n, lane);
     const uint32_t colw = legal_word_of(cur, n, lane);
     const uint32_t w0 = __shfl_sync(kFullMask, colw, x0), w1 = __shfl_sync(kFullMask, colw, x1);
     const uint32_t w = ((w0 >> y0) | (w1 << (n - y0))) & chunk_mask;
+    // prefix sum of the 32 chunk populations (each <= kMaxChunkBits < 32) by ballots, one per bit of the
+    // count: shuffles would queue on the shared-memory data pipe, which is what bounds this kernel
     const int c = __popc(w);
-    int incl = c;
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+    int incl = 0, total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFullMask, incl, o);
-      if (lane >= o) incl += t;
+    for (int k = 0; k < 5; ++k) {
+      const uint32_t bk = __ballot_sync(kFullMask, (c >> k) & 1);
+      incl += __popc(bk & le_mask) << k;
+      total += __popc(bk) << k;
     }
-    const int total = __shfl_sync(kFullMask, incl, 31);
     if (out_counts != nullptr && lane == 0) out_counts[env] = total;
-    if (out_actions != nullptr) {
-      // this chunk's cells, filled from both ends at once (two independent chains per trip; with one
-      // bit left both ends name the same slot and value); flat cell index == action
-      uint32_t rest = w;
-      T* lo = row + (incl - c);
-      T* hi = row + incl;
-      while (rest) {
-        const int b0 = __ffs(static_cast<int>(rest)) - 1;
-        const int b1 = 31 - __clz(static_cast<int>(rest));
-        rest &= rest - 1u;
-        rest &= ~(1u << b1);
-        *lo++ = static_cast<T>(first + b0);
-        *--hi = static_cast<T>(first + b1);
+    if (dst != nullptr) {
+      // flat cell index == action; bits past the chunk are zero, so the run needs no length test
+      uint16_t* slot = row + (incl - c);
+#pragma unroll
+      for (int j = 0; j < kMaxChunkBits; ++j) {
+        if ((w >> j) & 1u) {
+          *slot = static_cast<uint16_t>(first + j);
+          ++slot;
+        }
       }
       __syncwarp();
-      T* dst = out_actions + env * stride;
-      constexpr int kPerVec = 16 / static_cast<int>(sizeof(T));
-      int done = 0;
-      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      if (vec_ok) {
         const int nvec = total / kPerVec;
+#pragma unroll 1
         for (int v = lane; v < nvec; v += 32)
-          reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(row)[v];
-        done = nvec * kPerVec;
+          reinterpret_cast<uint4*>(dst)[v] = widen_actions<T>(row, v);
+        const int i = nvec * kPerVec + lane;  // fewer than kPerVec <= 8 entries are left
+        if (i < total) dst[i] = static_cast<T>(row[i]);
+      } else {
+#pragma unroll 1
+        for (int i = lane; i < total; i += 32) dst[i] = static_cast<T>(row[i]);
       }
-      for (int i = done + lane; i < total; i += 32) dst[i] = row[i];
       __syncwarp();  // the row is reused by the next env
+      dst += dst_step;
     }
     cur = nxt;
   }
@@ -356,6 +389,20 @@ inline int grid_for(int64_t items, int threads, int max_blocks = 148 * 64) {
   return static_cast<int>(blocks);
 }
 
+// Grid of a persistent kernel: exactly the blocks that are resident at once (SM count x occupancy), capped by
+// the work.  Every block then strides over the same share of the envs; a grid larger than one resident wave
+// would leave the last, partly filled wave running alone.
+template <typename Kernel>
+inline unsigned persistent_grid(Kernel kernel, int threads, int64_t items_per_block_pass, int64_t items) {
+  int dev = 0, sms = 148, per_sm = 1;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  return static_cast<unsigned>(grid_for(items, static_cast<int>(items_per_block_pass), sms * per_sm));
+}
+
 }  // namespace
 
 cudaError_t launch_reset(uint32_t* records, int64_t count, int n, cudaStream_t s) {
@@ -377,34 +424,39 @@ cudaError_t launch_legal_actions(const uint32_t* records, int64_t count, int n, 
                                  int64_t stride, int32_t* out_counts, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   const int threads = kLegalWarps * 32;
-  const unsigned blocks = static_cast<unsigned>(grid_for(count, kLegalWarps, 148 * 8));  // 8 resident blocks per SM
   const int rw = record_words(n);
-  if (elem_bytes == 2)
-    legal_actions_kernel<uint16_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
-                                                             static_cast<uint16_t*>(out_actions), stride, out_counts);
-  else if (elem_bytes == 4)
-    legal_actions_kernel<int32_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
-                                                            static_cast<int32_t*>(out_actions), stride, out_counts);
-  else
-    legal_actions_kernel<int64_t><<<blocks, threads, 0, s>>>(records, count, n, rw,
-                                                            static_cast<int64_t*>(out_actions), stride, out_counts);
+  if (elem_bytes == 2) {
+    const auto k = legal_actions_kernel<uint16_t>;
+    k<<<persistent_grid(k, threads, kLegalWarps, count), threads, 0, s>>>(
+        records, count, n, rw, static_cast<uint16_t*>(out_actions), stride, out_counts);
+  } else if (elem_bytes == 4) {
+    const auto k = legal_actions_kernel<int32_t>;
+    k<<<persistent_grid(k, threads, kLegalWarps, count), threads, 0, s>>>(
+        records, count, n, rw, static_cast<int32_t*>(out_actions), stride, out_counts);
+  } else {
+    const auto k = legal_actions_kernel<int64_t>;
+    k<<<persistent_grid(k, threads, kLegalWarps, count), threads, 0, s>>>(
+        records, count, n, rw, static_cast<int64_t*>(out_actions), stride, out_counts);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_legal_mask(const uint32_t* records, int64_t count, int n, uint8_t* out, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   const int threads = kLegalWarps * 32;
-  const unsigned blocks = static_cast<unsigned>(grid_for(count, kLegalWarps, 148 * 8));
   // the fast path needs word-aligned columns (n % 4 == 0) and 16-byte aligned rows (n*n % 16 == 0 then)
   const bool fast = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
   const int rw = record_words(n);
+  const auto go = [&](auto kernel) {
+    kernel<<<persistent_grid(kernel, threads, kLegalWarps, count), threads, 0, s>>>(records, count, n, rw, out);
+  };
   switch (fast ? n / 4 : 0) {
-    case 2: legal_mask_kernel<2><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
-    case 3: legal_mask_kernel<3><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
-    case 4: legal_mask_kernel<4><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
-    case 5: legal_mask_kernel<5><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
-    case 6: legal_mask_kernel<6><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
-    default: legal_mask_kernel<0><<<blocks, threads, 0, s>>>(records, count, n, rw, out); break;
+    case 2: go(legal_mask_kernel<2>); break;
+    case 3: go(legal_mask_kernel<3>); break;
+    case 4: go(legal_mask_kernel<4>); break;
+    case 5: go(legal_mask_kernel<5>); break;
+    case 6: go(legal_mask_kernel<6>); break;
+    default: go(legal_mask_kernel<0>); break;
   }
   return cudaGetLastError();
 }
@@ -433,11 +485,13 @@ cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, fl
   if (count <= 0) return cudaSuccess;
   const int rw = record_words(n);
   const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  const unsigned blocks = static_cast<unsigned>(grid_for(count, 1, 148 * 8));  // persistent: 8 blocks per SM
-  if (vec)
-    observation_kernel<true><<<blocks, kObsThreads, 0, s>>>(records, count, n, rw, out);
-  else
-    observation_kernel<false><<<blocks, kObsThreads, 0, s>>>(records, count, n, rw, out);
+  if (vec) {
+    const auto k = observation_kernel<true>;
+    k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+  } else {
+    const auto k = observation_kernel<false>;
+    k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+  }
   return cudaGetLastError();
 }
 
