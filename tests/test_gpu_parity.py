@@ -522,6 +522,47 @@ def test_playout_edge_cases(oracle_mod):
     batch.close()
 
 
+@pytest.mark.parametrize("n", [5, 7, 8, 13, 18, 24])
+def test_legal_list_every_width_stride_and_alignment(oracle_mod, n):
+    """K1 list kernel: uint16 / int32 / int64 actions, strides that do and do not keep rows 16-byte aligned,
+    a base pointer off the 16-byte grid; lists equal the oracle's, entries past the count keep their fill."""
+    import torch
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    og = oracle_mod.OracleGame(n)
+    E = 97
+    batch = TwixTBatch(n, E, 0, SEED)
+    # envs at different depths: env e plays e % 33 plies in one call (some games at n=5 are over by then)
+    depth_of = [e % 33 for e in range(E)]
+    for e in range(E):
+        if depth_of[e]:
+            batch.playout(e, 1, max_plies=depth_of[e], want_returns=False, want_lengths=False)
+    recs = batch.export_state()
+    want = []
+    for e in range(E):
+        st = og.new_initial_state()
+        st.playout_philox(SEED, e, depth_of[e])
+        assert np.array_equal(st.export_record(), recs[e])
+        want.append(st.legal_actions())
+    m = batch.max_legal_actions
+    dev = torch.device("cuda", 0)
+    for dtype, fill in ((torch.int16, -7), (torch.int32, -7), (torch.int64, -7)):
+        per_vec = 16 // torch.empty(0, dtype=dtype).element_size()
+        for stride in (m, m + 1, -(-m // per_vec) * per_vec, -(-m // per_vec) * per_vec + per_vec):
+            for off in (0, 1):
+                flat = torch.full((E * stride + 8,), fill, dtype=dtype, device=dev)
+                out = flat[off:off + E * stride].view(E, stride)
+                cnt = torch.zeros(E, dtype=torch.int32, device=dev)
+                batch.legal_actions(out_actions=out, out_counts=cnt)
+                got, c = out.cpu().numpy(), cnt.cpu().numpy()
+                for e in range(E):
+                    assert c[e] == len(want[e]), (n, dtype, stride, off, e)
+                    assert got[e, :c[e]].tolist() == want[e], (n, dtype, stride, off, e)
+                    assert (got[e, c[e]:] == fill).all(), (n, dtype, stride, off, e)
+                edge = flat.cpu().numpy()
+                assert (edge[:off] == fill).all() and (edge[off + E * stride:] == fill).all()
+    batch.close()
+
+
 def test_serialize_roundtrip_and_record_import(oracle_mod):
     """history (de)serialisation and packed-record import give the same state."""
     from twixt_for_open_spiel_b200 import load_game
