@@ -9,7 +9,6 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from . import build as _build
 
 _lib = None
 
@@ -81,6 +80,7 @@ OK, EINVAL, ECUDA, EILLEGAL, ENOMEM = 0, -1, -2, -3, -4
 
 
 def library_path() -> str:
+    from . import build as _build  # lazily: `python -m twixt_for_open_spiel_b200.build` imports this package first
     return _build.LIB
 
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
             fn.argtypes = argtypes
         _lib = lib
         return lib
+    from . import build as _build
     if not os.path.exists(_build.LIB) or (os.environ.get("TWIXT_B200_REBUILD") == "1"):
         _build.build(force=True)
     elif _build.needs_build():

@@ -49,12 +49,6 @@ namespace {
 #ifndef TW_PLAYOUT_THREADS
 #define TW_PLAYOUT_THREADS 128
 #endif
-#ifndef TW_EXP_CACHE_IN_SMEM
-#define TW_EXP_CACHE_IN_SMEM 0
-#endif
-#ifndef TW_EXP_LINK_ALWAYS
-#define TW_EXP_LINK_ALWAYS true
-#endif
 #ifndef TW_PLAYOUT_MIN_BLOCKS
 #define TW_PLAYOUT_MIN_BLOCKS 1
 #endif
@@ -85,14 +79,10 @@ struct PlayoutRef {
   // BSSY/BRA/BSYNC region (ten of them per move showed up as branch_resolving stalls), and redirecting
   // the store of the "false" lanes to a sink word measured slower than that
   __device__ __forceinline__ void st_if(bool c, int plane, int col, uint32_t v) {
-#if defined(TW_EXP_BRANCHY_ST)
-    if (c) st(plane, col, v);
-#else
     const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p + (plane * n() + col) * 32));
     asm volatile(
         "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp st.shared.u32 [%1], %2;\n\t}"
         :: "r"(static_cast<uint32_t>(c)), "r"(addr), "r"(v) : "memory");
-#endif
   }
   __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
@@ -117,7 +107,7 @@ struct PlayoutRef {
   // store->load round trip after a move); the run-time-size instantiation keeps them in shared memory
   // after the planes and the stack.
   static constexpr bool kCountCache = true;
-  static constexpr bool kCacheInRegs = NT > 0 && !TW_EXP_CACHE_IN_SMEM;
+  static constexpr bool kCacheInRegs = NT > 0;
   uint32_t cw[kCacheWords];
   __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
   __device__ __forceinline__ uint32_t cache_ld(int i) const { return kCacheInRegs ? cw[i] : *cache_word(i); }
@@ -323,7 +313,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       const int ln = legal_count(hn, n);
       int nx, ny;
       select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
-      const bool win = link_move<TW_EXP_LINK_ALWAYS>(b, pl, pend);
+      const bool win = link_move</*kAlways=*/true>(b, pl, pend);
       finish_move(h, pl, win);
       origin = flood_entry(pl.x, 1u << pl.y);
       ++step;
