@@ -142,11 +142,7 @@ struct LocalStack {
     if (c) push(e);
   }
   TW_HD uint32_t top() const { return v[sp - 1]; }
-  // after one cell of the top entry was taken: keep the entry with the remaining rows, or drop it
-  TW_HD void retop(bool keep, uint32_t e) {
-    if (keep) v[sp - 1] = e;
-    else --sp;
-  }
+  TW_HD void pop() { --sp; }
 };
 
 template <class B>
@@ -266,32 +262,32 @@ TW_HD uint32_t links_of(const B& b, int x, int y) {
 // visits of one env with the moves of the other envs of its warp instead of
 // making 31 lanes wait for one lane's whole flood.
 //
-// One visit: pop a cell, flag + push every linked neighbour that lacks the flag.
-// Word-parallel and straight-line: for each of the four neighbour COLUMNS the
-// (at most two) linked neighbour cells are formed directly as a row mask from
-// the link words -- an east link is a bit of this cell's own link word moved
-// to the target row, a west link is a bit of the neighbour column's link word
-// sitting AT the target row -- then masked with the flag word.  (Eight
-// data-dependent branches per visit cost more than they skipped, and the
-// per-direction formulation was 40 % more instructions.)
+// One visit: pop an ENTRY -- all its cells of one column at once -- and flag +
+// push every linked neighbour that lacks the flag.  Word-parallel and
+// straight-line: for each of the four neighbour COLUMNS the linked neighbour
+// cells are formed directly as a row mask from the link words -- the east
+// links are bits of this column's own link words (at the entry's rows) moved
+// to their target rows, the west links are bits of the neighbour column's link
+// words sitting AT the target rows -- then masked with the flag word.  A row
+// shifted off the board meets no link bit.  (Eight data-dependent branches per
+// visit cost more than they skipped, and the per-direction formulation was
+// 40 % more instructions.)
 template <class B, class Stack>
 TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
-  // take the lowest cell of the top entry
   const uint32_t e = stk.top();
+  stk.pop();
   const uint32_t rows = e & 0x00FFFFFFu;
-  const int cx = static_cast<int>(e >> 24), cy = tw_ctz(rows);
-  const uint32_t bit = 1u << cy;
-  stk.retop((rows & (rows - 1u)) != 0u, e & ~bit);
-  // links stored at this cell (it is their west endpoint): NNE, ENE, ESE, SSE
-  const uint32_t own0 = b.ld(P_LINK0 + 0, cx) & bit, own1 = b.ld(P_LINK0 + 1, cx) & bit;
-  const uint32_t own2 = b.ld(P_LINK0 + 2, cx) & bit, own3 = b.ld(P_LINK0 + 3, cx) & bit;
+  const int cx = static_cast<int>(e >> 24);
+  // links stored at these cells (they are their west endpoints): NNE, ENE, ESE, SSE
+  const uint32_t own0 = b.ld(P_LINK0 + 0, cx) & rows, own1 = b.ld(P_LINK0 + 1, cx) & rows;
+  const uint32_t own2 = b.ld(P_LINK0 + 2, cx) & rows, own3 = b.ld(P_LINK0 + 3, cx) & rows;
   // linked neighbours per column, as row masks
-  const uint32_t e1 = (own0 << 2) | (own3 >> 2);                      // (cx+1, cy+2) NNE, (cx+1, cy-2) SSE
-  const uint32_t e2 = (own1 << 1) | (own2 >> 1);                      // (cx+2, cy+1) ENE, (cx+2, cy-1) ESE
-  const uint32_t w1 = (b.ld_guard(P_LINK0 + 0, cx - 1) & (bit >> 2)) |   // NNE link of (cx-1, cy-2)
-                      (b.ld_guard(P_LINK0 + 3, cx - 1) & (bit << 2));    // SSE link of (cx-1, cy+2)
-  const uint32_t w2 = (b.ld_guard(P_LINK0 + 1, cx - 2) & (bit >> 1)) |   // ENE link of (cx-2, cy-1)
-                      (b.ld_guard(P_LINK0 + 2, cx - 2) & (bit << 1));    // ESE link of (cx-2, cy+1)
+  const uint32_t e1 = (own0 << 2) | (own3 >> 2);                       // (cx+1, cy+2) NNE, (cx+1, cy-2) SSE
+  const uint32_t e2 = (own1 << 1) | (own2 >> 1);                       // (cx+2, cy+1) ENE, (cx+2, cy-1) ESE
+  const uint32_t w1 = (b.ld_guard(P_LINK0 + 0, cx - 1) & (rows >> 2)) |   // NNE links of (cx-1, cy-2)
+                      (b.ld_guard(P_LINK0 + 3, cx - 1) & (rows << 2));    // SSE links of (cx-1, cy+2)
+  const uint32_t w2 = (b.ld_guard(P_LINK0 + 1, cx - 2) & (rows >> 1)) |   // ENE links of (cx-2, cy-1)
+                      (b.ld_guard(P_LINK0 + 2, cx - 2) & (rows << 1));    // ESE links of (cx-2, cy+1)
   const uint32_t f_e1 = b.ld_guard(flag_plane, cx + 1), f_e2 = b.ld_guard(flag_plane, cx + 2);
   const uint32_t f_w1 = b.ld_guard(flag_plane, cx - 1), f_w2 = b.ld_guard(flag_plane, cx - 2);
   const uint32_t n_e1 = e1 & ~f_e1, n_e2 = e2 & ~f_e2, n_w1 = w1 & ~f_w1, n_w2 = w2 & ~f_w2;

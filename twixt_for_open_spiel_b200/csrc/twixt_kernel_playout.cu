@@ -148,11 +148,7 @@ struct SmemStack {
     overflow |= c && !room;
   }
   __device__ __forceinline__ uint32_t top() const { return base[(sp - 1) * 32]; }
-  // after one cell of the top entry was taken: keep the entry with the remaining rows, or drop it
-  __device__ __forceinline__ void retop(bool keep, uint32_t e) {
-    if (keep) base[(sp - 1) * 32] = e;
-    sp -= keep ? 0 : 1;
-  }
+  __device__ __forceinline__ void pop() { --sp; }
 };
 
 // resident blocks per SM the register allocation should allow: what shared memory allows for that size

@@ -25,7 +25,19 @@ namespace {
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kFloodStack = 48;
 
-__device__ __forceinline__ uint4 ldg128(const uint32_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// Read-only loads of a PART of a record, with the 64-byte L2 fetch-size hint: the kernels below use the
+// first 16..208 bytes of each 880-byte record, and the default 128-byte fetch pulled 320 bytes per env out
+// of DRAM where 256 do (legal mask: 0.168 -> 0.162 ms per 1 Mi envs).
+__device__ __forceinline__ uint4 ldg128(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 
 // ---------------------------------------------------------------- reset ---
 // Board::Board (twixtboard.cc:168-174): empty board, both legal lists full.
@@ -69,10 +81,10 @@ struct LegalInputs {
 
 __device__ __forceinline__ LegalInputs legal_fetch(const uint32_t* rec, int n, int lane) {
   LegalInputs in;
-  in.hw = ldg128(rec);
   const int col = lane < n ? lane : 0;
-  in.red = __ldg(rec + kHeaderWords + col);
-  in.blue = __ldg(rec + kHeaderWords + n + col);
+  in.hw = ldg128(rec);
+  in.red = ldg32(rec + kHeaderWords + col);
+  in.blue = ldg32(rec + kHeaderWords + n + col);
   return in;
 }
 
