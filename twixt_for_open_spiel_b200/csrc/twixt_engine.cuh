@@ -273,9 +273,7 @@ TW_HD uint32_t links_of(const B& b, int x, int y) {
 // visit cost more than they skipped, and the per-direction formulation was
 // 40 % more instructions.)
 template <class B, class Stack>
-TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
-  const uint32_t e = stk.top();
-  stk.pop();
+TW_HD void flood_visit_entry(B& b, int flag_plane, Stack& stk, uint32_t e) {
   const uint32_t rows = e & 0x00FFFFFFu;
   const int cx = static_cast<int>(e >> 24);
   // links stored at these cells (they are their west endpoints): NNE, ENE, ESE, SSE
@@ -299,6 +297,14 @@ TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
   stk.push_if(n_e2 != 0u, flood_entry(cx + 2, n_e2));
   stk.push_if(n_w1 != 0u, flood_entry(cx - 1, n_w1));
   stk.push_if(n_w2 != 0u, flood_entry(cx - 2, n_w2));
+}
+
+// ... of the entry on top of the stack
+template <class B, class Stack>
+TW_HD void flood_visit(B& b, int flag_plane, Stack& stk) {
+  const uint32_t e = stk.top();
+  stk.pop();
+  flood_visit_entry(b, flag_plane, stk, e);
 }
 
 // If the stack overflowed, the dropped cells are recovered by closing the

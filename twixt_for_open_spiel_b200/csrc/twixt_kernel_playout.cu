@@ -92,15 +92,14 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
   __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
-  // One branch around all three columns: inside it the REDs are unconditional (OR-ing zero bits is
-  // harmless, and a column left of the board only ever has zero bits: its address is clamped), because
-  // ptxas turns every conditional RED into its own BSSY/BRA/BSYNC region.
+  // Three UNCONDITIONAL reductions per move: OR-ing zero bits is harmless (and a column left of the board
+  // only ever gets zero bits: its address is clamped).  ptxas cannot predicate a RED -- every conditional
+  // one becomes its own branch region (three of them cost 9 %), and even one branch around all three
+  // (taken by half of the moves) was 2.5 % slower than always issuing them.
   __device__ __forceinline__ void or_blocked3(int x, const uint32_t blk[3]) {
-    if (blk[0] | blk[1] | blk[2]) {
-      atomicOr(gblk + x, blk[0]);
-      atomicOr(gblk + max(x - 1, 0), blk[1]);
-      atomicOr(gblk + max(x - 2, 0), blk[2]);
-    }
+    atomicOr(gblk + x, blk[0]);
+    atomicOr(gblk + max(x - 1, 0), blk[1]);
+    atomicOr(gblk + max(x - 2, 0), blk[2]);
   }
   // per-column count cache (twixt_engine.cuh, count_cache_*).  With a compile-time board size every index
   // into it is static after unrolling, so the six words live in REGISTERS (no load before a selection, no
@@ -149,6 +148,13 @@ struct SmemStack {
   }
   __device__ __forceinline__ uint32_t top() const { return base[(sp - 1) * 32]; }
   __device__ __forceinline__ void pop() { --sp; }
+  // pop the top entry, or take `otherwise` if there is none (branch-free: the load address is clamped)
+  __device__ __forceinline__ uint32_t top_or(uint32_t otherwise) {
+    const bool have = sp > 0;
+    const uint32_t t = base[(have ? sp - 1 : 0) * 32];
+    sp -= have ? 1 : 0;
+    return have ? t : otherwise;
+  }
 };
 
 // resident blocks per SM the register allocation should allow: what shared memory allows for that size
@@ -318,14 +324,16 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       sy = ny;
     }
     // ---- FLOOD: one visit for the lanes that owe border-flag propagation -----
-    if (stk.empty() && pend != 0u) {
+    // One branch for "start the next pending flood" and "continue the running one": a lane whose stack is
+    // empty but which owes a flood visits the new peg itself (`origin`, no trip through the stack), the
+    // others visit the entry on top of their stack.
+    if (!stk.empty() || pend != 0u) {
+      const bool begin = stk.empty();
       const bool start = (pend & kFloodStart) != 0u;
-      fplane = start ? P_START : P_END;
-      pend &= start ? ~kFloodStart : ~kFloodEnd;
-      stk.push(origin);
-    }
-    if (!stk.empty()) {
-      flood_visit(b, fplane, stk);
+      fplane = begin ? (start ? P_START : P_END) : fplane;
+      pend &= begin ? (start ? ~kFloodStart : ~kFloodEnd) : ~0u;
+      const uint32_t e = stk.top_or(origin);
+      flood_visit_entry(b, fplane, stk, e);
       if (stk.empty() && stk.overflow) {
         flood_closure(b, ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE, fplane);
         stk.overflow = false;
