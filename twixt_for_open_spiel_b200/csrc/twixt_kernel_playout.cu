@@ -294,13 +294,32 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     else exhausted = true;
   }
 
-  for (uint32_t it = 1; __any_sync(kFullMask, idx >= 0); ++it) {
-    if (loading) finish_take();
-    if ((it & 3u) == 0u) {  // warp-uniform: every lane that has moved into its second block gets the next one
+  for (uint32_t it = 1;; ++it) {
+    if ((it & 3u) == 0u) {  // warp-uniform
+      // a lane only runs out of envs in the rare block below, so looking every fourth iteration is enough
+      if (!__any_sync(kFullMask, idx >= 0)) break;
+      // every lane that has moved into its second block of random words gets the next one
       if (static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {  // step+1 = next word to be consumed
         rq += 1u;
         ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2]; ra[3] = rb[3];
         philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
+      }
+    }
+    // ---- RARE (one branch region): an env whose copy was started an iteration ago is unpacked; a finished
+    // env goes back to HBM and the lane starts copying the next one
+    {
+      const bool done = idx >= 0 && !loading && !playing && pend == 0u && stk.empty();
+      if (loading || done) {
+        if (loading) {
+          finish_take();
+        } else {
+          give();
+          if (!exhausted) {
+            const int64_t e = preassigned + static_cast<int64_t>(atomicAdd(a.tickets, 1ull));
+            if (e < a.count) begin_take(e);
+            else exhausted = true;
+          }
+        }
       }
     }
     // ---- MOVE: lanes with no flood work left make their next move -----------
@@ -337,15 +356,6 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       if (stk.empty() && stk.overflow) {
         flood_closure(b, ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE, fplane);
         stk.overflow = false;
-      }
-    }
-    // ---- RETIRE + REFILL: a finished env goes back to HBM, the lane takes the next one
-    if (idx >= 0 && !loading && !playing && pend == 0u && stk.empty()) {
-      give();
-      if (!exhausted) {
-        const int64_t e = preassigned + static_cast<int64_t>(atomicAdd(a.tickets, 1ull));
-        if (e < a.count) begin_take(e);
-        else exhausted = true;
       }
     }
   }
