@@ -54,6 +54,9 @@ TW_HD int tw_ctz(uint32_t v) {
 #endif
 }
 
+TW_HD int tw_min(int a, int b) { return a < b ? a : b; }
+TW_HD int tw_max(int a, int b) { return a > b ? a : b; }
+
 // Compass offsets (twixtcell.h:58-68), biased by +2 and packed one nibble per
 // direction so a lookup is a shift and a mask.
 TW_HD int dir_dx(int d) { return static_cast<int>((0x10013443u >> (4 * d)) & 15u) - 2; }
@@ -286,8 +289,11 @@ TW_HD void flood_visit_entry(B& b, int flag_plane, Stack& stk, uint32_t e) {
                       (b.ld_guard(P_LINK0 + 3, cx - 1) & (rows << 2));    // SSE links of (cx-1, cy+2)
   const uint32_t w2 = (b.ld_guard(P_LINK0 + 1, cx - 2) & (rows >> 1)) |   // ENE links of (cx-2, cy-1)
                       (b.ld_guard(P_LINK0 + 2, cx - 2) & (rows << 1));    // ESE links of (cx-2, cy+1)
-  const uint32_t f_e1 = b.ld_guard(flag_plane, cx + 1), f_e2 = b.ld_guard(flag_plane, cx + 2);
-  const uint32_t f_w1 = b.ld_guard(flag_plane, cx - 1), f_w2 = b.ld_guard(flag_plane, cx - 2);
+  // a neighbour column off the board has no linked cells (e1.. are zero there), so its flag word may be
+  // any word: clamp the column instead of guarding the load (guards compiled into a branch region)
+  const int n1 = b.n() - 1;
+  const uint32_t f_e1 = b.ld(flag_plane, tw_min(cx + 1, n1)), f_e2 = b.ld(flag_plane, tw_min(cx + 2, n1));
+  const uint32_t f_w1 = b.ld(flag_plane, tw_max(cx - 1, 0)), f_w2 = b.ld(flag_plane, tw_max(cx - 2, 0));
   const uint32_t n_e1 = e1 & ~f_e1, n_e2 = e2 & ~f_e2, n_w1 = w1 & ~f_w1, n_w2 = w2 & ~f_w2;
   b.st_if(n_e1 != 0u, flag_plane, cx + 1, f_e1 | n_e1);
   b.st_if(n_e2 != 0u, flag_plane, cx + 2, f_e2 | n_e2);
@@ -364,26 +370,35 @@ struct Placement {
   uint32_t action; // the action as played
 };
 
+// The swap (twixtboard.cc:465-475): blue answers red's first move with the same action.  The red peg is
+// taken back (UndoFirstMove, 450-455) and (x,y) becomes the cell turned by 90 degrees, where the blue peg
+// goes (471-473).
+TW_HD bool is_swap(const Header& h, uint32_t action) { return h.ply == 1u && action == h.move_one; }
+
 template <class B>
+TW_HD void swap_first_move(B& b, Header& h, int& x, int& y) {
+  const int n = b.n();
+  b.st_pegs(P_RED, x, b.ld_pegs(P_RED, x) & ~(1u << y));
+  b.note_peg(x, y, -1);
+  b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
+  b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
+  h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
+  h.cnt[kBlue] += (y >= 1 && y <= n - 2) ? 1 : 0;
+  h.swapped = 1u;
+  const int rx = y, ry = n - 1 - x;
+  x = rx;
+  y = ry;
+}
+
+// kSwapDone: the caller has already run swap_first_move for a swapping action (the fused playout kernel
+// does it in its rare-events block, so that the per-move code has no branch for it).
+template <bool kSwapDone = false, class B>
 TW_HD Placement begin_move(B& b, Header& h, int x, int y) {
   const int n = b.n();
   Placement p;
   p.player = static_cast<int>(h.ply & 1u);
-  p.action = static_cast<uint32_t>(x * n + y);
-  if (h.ply == 1u && p.action == h.move_one) {
-    // swap: take the red peg back (UndoFirstMove, 450-455) and put a blue one
-    // on the cell turned by 90 degrees (471-473)
-    b.st_pegs(P_RED, x, b.ld_pegs(P_RED, x) & ~(1u << y));
-    b.note_peg(x, y, -1);
-    b.st(P_START, x, b.ld(P_START, x) & ~(1u << y));
-    b.st(P_END, x, b.ld(P_END, x) & ~(1u << y));
-    h.cnt[kRed] += (x >= 1 && x <= n - 2) ? 1 : 0;
-    h.cnt[kBlue] += (y >= 1 && y <= n - 2) ? 1 : 0;
-    h.swapped = 1u;
-    const int rx = y, ry = n - 1 - x;
-    x = rx;
-    y = ry;
-  }
+  p.action = static_cast<uint32_t>(x * n + y);  // only read for the first move of a game
+  if (!kSwapDone && is_swap(h, p.action)) swap_first_move(b, h, x, y);
   p.x = x;
   p.y = y;
   const int own = p.player == kRed ? P_RED : P_BLUE;

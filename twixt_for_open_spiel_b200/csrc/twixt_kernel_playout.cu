@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
   uint32_t pend = 0, origin = 0, swapped_before = 0;
   int fplane = P_START;
   bool playing = false, open_at_start = false;
+  // the chosen cell is the swap (blue repeats red's first action): its first half -- taking the red peg
+  // back and turning the cell -- runs in the rare-events block, so MOVE has no branch for it
+  bool swap_next = false;
+  int sact = 0;  // the chosen action as played (only the trace needs it: a swap turns (sx, sy))
   // ---- per-lane totals over all envs this lane plays -------------------------
   uint32_t t_plies = 0, t_games = 0, t_red = 0, t_blue = 0, t_draws = 0, t_swaps = 0, t_maxlen = 0;
 
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     playing = open_at_start && a.max_plies > 0;
     if (playing)
       select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
+    sact = sx * n + sy;
+    swap_next = playing && is_swap(h, static_cast<uint32_t>(sact));
     loading = false;
   };
 
@@ -309,10 +315,10 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     // env goes back to HBM and the lane starts copying the next one
     {
       const bool done = idx >= 0 && !loading && !playing && pend == 0u && stk.empty();
-      if (loading || done) {
+      if (loading || done || swap_next) {
         if (loading) {
           finish_take();
-        } else {
+        } else if (done) {
           give();
           if (!exhausted) {
             const int64_t e = preassigned + static_cast<int64_t>(atomicAdd(a.tickets, 1ull));
@@ -320,13 +326,17 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
             else exhausted = true;
           }
         }
+        if (swap_next) {  // possibly set by finish_take just now: a game taken over at ply 1
+          swap_first_move(b, h, sx, sy);
+          swap_next = false;
+        }
       }
     }
     // ---- MOVE: lanes with no flood work left make their next move -----------
     if (playing && pend == 0u && stk.empty()) {
       if (kTrace && step < a.trace_plies)
-        a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(sx * n + sy);
-      const Placement pl = begin_move(b, h, sx, sy);
+        a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(sact);
+      const Placement pl = begin_move</*kSwapDone=*/true>(b, h, sx, sy);
       // choose the following move now (speculatively: unused if this move ends the game); it only reads the
       // peg planes and the count cache, which begin_move has just brought up to date
       Header hn = h;
@@ -341,6 +351,8 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
       playing = h.result == kOpen && step < a.max_plies;
       sx = nx;
       sy = ny;
+      sact = nx * n + ny;
+      swap_next = playing && is_swap(h, static_cast<uint32_t>(sact));
     }
     // ---- FLOOD: one visit for the lanes that owe border-flag propagation -----
     // One branch for "start the next pending flood" and "continue the running one": a lane whose stack is
