@@ -37,6 +37,7 @@ def _build(stack):
     he.he_observation.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     he.he_playout.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     he.he_playout_cached.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    he.he_playout_smem.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     he.he_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     he.he_select_bit.argtypes = [C.c_uint32, C.c_int]
     return he
@@ -106,21 +107,27 @@ def test_rules_match_oracle(he, oracle_mod, n):
             assert he.he_apply(P(rec), n, a) == 0
             st.apply_action(a)
             ply += 1
-    # the fused-playout policy: same Philox stream, same k-th legal pick -- with the plain column scan
-    # and with the kernel's structure (per-column count cache, moves interleaved with flood visits)
-    for fn in (he.he_playout, he.he_playout_cached):
-        for s in range(12):
+    # the fused-playout policy: same Philox stream, same k-th legal pick -- with the plain column scan, with
+    # the kernel's structure (per-column count cache, moves interleaved with flood visits, swap run ahead of
+    # the move) and with that structure on the kernel's shared-memory layout (no bounds tests on the link
+    # window).  Small boards get enough streams to contain swaps (1 game in n(n-2)).
+    swaps = 0
+    for fn in (he.he_playout, he.he_playout_cached, he.he_playout_smem):
+        for s in range(90 if n <= 6 else 12):
             rec = np.zeros(R, dtype=np.uint32)
             he.he_init(P(rec), n)
             st = og.new_initial_state()
-            if s % 3 == 2:  # from a mid-game position
-                pre = st.playout_philox(7, s, 2 + s)
+            if s % 3 == 2:  # from a mid-game position (s = 5, 11, ..: taken over at ply 1, before a possible swap)
+                pre = st.playout_philox(7, s, 1 if s % 6 == 5 else 2 + s % 40)
                 for a in pre:
                     assert he.he_apply(P(rec), n, a) == 0
             acts = np.zeros(n * n, dtype=np.int64)
             L = fn(P(rec), n, 0x7477697854, s + (n << 33), 1 << 30, P(acts))
             assert acts[:L].tolist() == st.playout_philox(0x7477697854, s + (n << 33)), (n, s)
             assert np.array_equal(rec, st.export_record())
+            swaps += int(rec[1] >> 2) & 1
+    if n <= 6:
+        assert swaps >= 3  # the swap path was really taken
 
 
 def test_rules_match_reference_generated_fixture(he):

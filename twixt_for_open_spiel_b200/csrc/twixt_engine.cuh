@@ -107,6 +107,15 @@ struct RecordRef {
   TW_HD uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
+  // Two relaxed reads for the hot straight-line code, which an accessor may implement WITHOUT a bounds
+  // test if its storage allows (the fused playout kernel's shared-memory layout does):
+  //  ld_link  link word of column `col` >= -3: must read as empty at column -1; at every other off-board
+  //           column the callers only use it for targets that are off the board themselves (link_move:
+  //           a target in column x+dx reads west endpoints in x+dx-1 .. x+dx+1 clipped to x-3 .. x+1,
+  //           twixt_crossing.inc, so a target on the board never looks left of column -1)
+  //  ld_any   word whose value the caller ignores when the column is off the board
+  TW_HD uint32_t ld_link(int plane, int col) const { return ld_guard(plane, col); }
+  TW_HD uint32_t ld_any(int plane, int col) const { return ld_guard(plane, col); }
   // the two peg planes (P_RED / P_BLUE) are the hot ones: an accessor may keep them
   // in faster memory than the rest, so the rules name them separately
   TW_HD uint32_t ld_pegs(int plane, int col) const { return ld(plane, col); }
@@ -146,6 +155,8 @@ struct LocalStack {
   }
   TW_HD uint32_t top() const { return v[sp - 1]; }
   TW_HD void pop() { --sp; }
+  // pop the top entry, or take `otherwise` if there is none
+  TW_HD uint32_t top_or(uint32_t otherwise) { return sp > 0 ? v[--sp] : otherwise; }
 };
 
 template <class B>
@@ -285,15 +296,13 @@ TW_HD void flood_visit_entry(B& b, int flag_plane, Stack& stk, uint32_t e) {
   // linked neighbours per column, as row masks
   const uint32_t e1 = (own0 << 2) | (own3 >> 2);                       // (cx+1, cy+2) NNE, (cx+1, cy-2) SSE
   const uint32_t e2 = (own1 << 1) | (own2 >> 1);                       // (cx+2, cy+1) ENE, (cx+2, cy-1) ESE
-  const uint32_t w1 = (b.ld_guard(P_LINK0 + 0, cx - 1) & (rows >> 2)) |   // NNE links of (cx-1, cy-2)
-                      (b.ld_guard(P_LINK0 + 3, cx - 1) & (rows << 2));    // SSE links of (cx-1, cy+2)
+  const uint32_t w1 = (b.ld_link(P_LINK0 + 0, cx - 1) & (rows >> 2)) |    // NNE links of (cx-1, cy-2)
+                      (b.ld_link(P_LINK0 + 3, cx - 1) & (rows << 2));     // SSE links of (cx-1, cy+2)
   const uint32_t w2 = (b.ld_guard(P_LINK0 + 1, cx - 2) & (rows >> 1)) |   // ENE links of (cx-2, cy-1)
                       (b.ld_guard(P_LINK0 + 2, cx - 2) & (rows << 1));    // ESE links of (cx-2, cy+1)
-  // a neighbour column off the board has no linked cells (e1.. are zero there), so its flag word may be
-  // any word: clamp the column instead of guarding the load (guards compiled into a branch region)
-  const int n1 = b.n() - 1;
-  const uint32_t f_e1 = b.ld(flag_plane, tw_min(cx + 1, n1)), f_e2 = b.ld(flag_plane, tw_min(cx + 2, n1));
-  const uint32_t f_w1 = b.ld(flag_plane, tw_max(cx - 1, 0)), f_w2 = b.ld(flag_plane, tw_max(cx - 2, 0));
+  // a neighbour column off the board has no linked cells (e1 .. w2 are empty there): its flag word is ignored
+  const uint32_t f_e1 = b.ld_any(flag_plane, cx + 1), f_e2 = b.ld_any(flag_plane, cx + 2);
+  const uint32_t f_w1 = b.ld_any(flag_plane, cx - 1), f_w2 = b.ld_any(flag_plane, cx - 2);
   const uint32_t n_e1 = e1 & ~f_e1, n_e2 = e2 & ~f_e2, n_w1 = w1 & ~f_w1, n_w2 = w2 & ~f_w2;
   b.st_if(n_e1 != 0u, flag_plane, cx + 1, f_e1 | n_e1);
   b.st_if(n_e2 != 0u, flag_plane, cx + 2, f_e2 | n_e2);
@@ -447,11 +456,11 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
 #pragma unroll
 #endif
       for (int pl = 0; pl < 4; ++pl) {
-        lw.w[pl][c] = b.ld_guard(P_LINK0 + pl, x - 3 + c);
+        lw.w[pl][c] = b.ld_link(P_LINK0 + pl, x - 3 + c);
         ly.w[pl][c] = (lw.w[pl][c] << 5) >> y;  // row y+oy at bit oy+5
       }
-      fs[c] = b.ld_guard(P_START, x - 2 + c);
-      fe[c] = b.ld_guard(P_END, x - 2 + c);
+      fs[c] = b.ld_any(P_START, x - 2 + c);  // only read under made[c], which is empty off the board
+      fe[c] = b.ld_any(P_END, x - 2 + c);
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll

@@ -72,8 +72,17 @@ struct PlayoutRef {
   uint32_t* gblk;  // global: the record's P_BLOCKED words
   int n_rt;
   __device__ __forceinline__ int n() const { return NT > 0 ? NT : n_rt; }
+  // Shared-memory order of the planes: BLUE, RED, the four link planes, START, END (the record has RED
+  // first).  With it the word in front of every link plane is always zero -- red never stands in column
+  // n-1 (blue's end line), and a link plane holds links at their WEST endpoint, so its column n-1 is
+  // empty -- which is what ld_link needs: the rules' link-window loads carry no bounds test at all.  Words
+  // read further off the board belong to this env's neighbouring planes or its stack words.
   __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
   __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
+  __device__ __forceinline__ uint32_t ld_link(int plane, int col) const { return ld(plane, col); }
+  __device__ __forceinline__ uint32_t ld_any(int plane, int col) const { return ld(plane, col); }
+  // record word (after the header) -> shared-memory word
+  __device__ __forceinline__ int smem_word(int w) const { return w < n() ? w + n() : (w < 2 * n() ? w - n() : w); }
   __device__ __forceinline__ uint32_t* sink() const { return p + (kSmemPlanes * n() + kStackWords + kCacheWords) * 32; }
   // conditional plane store as ONE predicated st.shared: the compiler turns `if (c) st(...)` into a
   // BSSY/BRA/BSYNC region (ten of them per move showed up as branch_resolving stalls), and redirecting
@@ -87,9 +96,9 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld_guard(int plane, int col) const {
     return (static_cast<unsigned>(col) < static_cast<unsigned>(n())) ? ld(plane, col) : 0u;
   }
-  __device__ __forceinline__ uint32_t ld_pegs(int plane, int col) const { return ld(plane, col); }
-  __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { st(plane, col, v); }
-  __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane, col); }
+  __device__ __forceinline__ uint32_t ld_pegs(int plane, int col) const { return ld(plane ^ 1, col); }
+  __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { st(plane ^ 1, col, v); }
+  __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane ^ 1, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
   __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
   // Three UNCONDITIONAL reductions per move: OR-ing zero bits is harmless (and a column left of the board
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     idx = e;
     grec = a.records + e * rw;
     for (int w = 0; w < kHeaderWords; ++w) __pipeline_memcpy_async(stk.base + w * 32, grec + w, 4);
-    for (int w = 0; w < kSmemPlanes * n; ++w) __pipeline_memcpy_async(mine + w * 32, grec + kHeaderWords + w, 4);
+    for (int w = 0; w < kSmemPlanes * n; ++w) __pipeline_memcpy_async(mine + b.smem_word(w) * 32, grec + kHeaderWords + w, 4);
     __pipeline_commit();
     loading = true;
     playing = false;
@@ -267,10 +276,10 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     dst[0] = hw;
     for (int q = 0; q < plane_quads; ++q) {
       uint4 v;
-      v.x = mine[(4 * q + 0) * 32];
-      v.y = mine[(4 * q + 1) * 32];
-      v.z = mine[(4 * q + 2) * 32];
-      v.w = mine[(4 * q + 3) * 32];
+      v.x = mine[b.smem_word(4 * q + 0) * 32];
+      v.y = mine[b.smem_word(4 * q + 1) * 32];
+      v.z = mine[b.smem_word(4 * q + 2) * 32];
+      v.w = mine[b.smem_word(4 * q + 3) * 32];
       dst[1 + q] = v;
     }
     if (a.out_returns != nullptr) {
