@@ -245,24 +245,31 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     __pipeline_wait_prior(0);
     unpack_header(stk.base[0], stk.base[32], stk.base[64], stk.base[96], h);
     b.gblk = grec + kHeaderWords + P_BLOCKED * n;
-    if (h.ply == 0u) {  // a fresh game has no pegs: skip the 2n popcounts
-#pragma unroll
-      for (int i = 0; i < kCacheWords; ++i) b.cache_st(i, 0u);
-    } else {
-      count_cache_build(b);
-    }
     const uint64_t stream = a.stream_ids != nullptr ? a.stream_ids[idx] : a.stream_base + static_cast<uint64_t>(idx);
     s_lo = static_cast<uint32_t>(stream);
     s_hi = static_cast<uint32_t>(stream >> 32);
     step = 0;
-    rq = 0;
-    philox4x32_10(s_lo, s_hi, 0u, 0u, k_lo, k_hi, ra);
-    philox4x32_10(s_lo, s_hi, 1u, 0u, k_lo, k_hi, rb);
+    // Only the first block of random words is made here, where one lane runs alone: it is parked as the
+    // SECOND buffered block of block number -1, so the warp-wide refresh below (at most three iterations
+    // away, before word 4 is needed) shifts it into place and makes block 1 together with the other lanes'.
+    rq = 0xFFFFFFFFu;
+    philox4x32_10(s_lo, s_hi, 0u, 0u, k_lo, k_hi, rb);
     swapped_before = h.swapped;
     open_at_start = h.result == kOpen;
     playing = open_at_start && a.max_plies > 0;
-    if (playing)
-      select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
+    if (h.ply == 0u) {
+      // a fresh game: no pegs to count, and red's k-th legal cell is known in closed form (every row of
+      // the columns 1 .. n-2, twixtboard.cc:252-276)
+#pragma unroll
+      for (int i = 0; i < kCacheWords; ++i) b.cache_st(i, 0u);
+      const int k = static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(n * (n - 2))));
+      sx = 1 + k / n;
+      sy = k - (sx - 1) * n;
+    } else {
+      count_cache_build(b);
+      if (playing)
+        select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
+    }
     sact = sx * n + sy;
     swap_next = playing && is_swap(h, static_cast<uint32_t>(sact));
     loading = false;
@@ -310,16 +317,6 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
   }
 
   for (uint32_t it = 1;; ++it) {
-    if ((it & 3u) == 0u) {  // warp-uniform
-      // a lane only runs out of envs in the rare block below, so looking every fourth iteration is enough
-      if (!__any_sync(kFullMask, idx >= 0)) break;
-      // every lane that has moved into its second block of random words gets the next one
-      if (static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {  // step+1 = next word to be consumed
-        rq += 1u;
-        ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2]; ra[3] = rb[3];
-        philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
-      }
-    }
     // ---- RARE (one branch region): an env whose copy was started an iteration ago is unpacked; a finished
     // env goes back to HBM and the lane starts copying the next one
     {
@@ -339,6 +336,16 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
           swap_first_move(b, h, sx, sy);
           swap_next = false;
         }
+      }
+    }
+    if ((it & 3u) == 0u) {  // warp-uniform
+      // a lane only runs out of envs in the rare block above, so looking every fourth iteration is enough
+      if (!__any_sync(kFullMask, idx >= 0)) break;
+      // every lane that has moved into its second block of random words gets the next one
+      if (static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {  // step+1 = next word to be consumed
+        rq += 1u;
+        ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2]; ra[3] = rb[3];
+        philox4x32_10(s_lo, s_hi, rq + 1u, 0u, k_lo, k_hi, rb);
       }
     }
     // ---- MOVE: lanes with no flood work left make their next move -----------
