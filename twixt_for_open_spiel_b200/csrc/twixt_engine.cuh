@@ -462,9 +462,6 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
       fs[c] = b.ld_any(P_START, x - 2 + c);  // only read under made[c], which is empty off the board
       fe[c] = b.ld_any(P_END, x - 2 + c);
     }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
     // crossed[c]: cells of column x-2+c the link to which would be crossed, as row masks
     uint32_t crossed[5] = {0u, 0u, 0u, 0u, 0u};
 #if defined(__CUDA_ARCH__)

@@ -141,10 +141,6 @@ struct SmemStack {
   int sp;
   bool overflow;
   __device__ __forceinline__ bool empty() const { return sp == 0; }
-  __device__ __forceinline__ void push(uint32_t c) {
-    if (sp < kStackWords) base[(sp++) * 32] = c;
-    else overflow = true;
-  }
   uint32_t* sink;  // the lane's sink word: where a refused entry is written
   // branch-free conditional push
   __device__ __forceinline__ void push_if(bool c, uint32_t cell) {
@@ -155,8 +151,6 @@ struct SmemStack {
     sp += doit ? 1 : 0;
     overflow |= c && !room;
   }
-  __device__ __forceinline__ uint32_t top() const { return base[(sp - 1) * 32]; }
-  __device__ __forceinline__ void pop() { --sp; }
   // pop the top entry, or take `otherwise` if there is none (branch-free: the load address is clamped)
   __device__ __forceinline__ uint32_t top_or(uint32_t otherwise) {
     const bool have = sp > 0;
