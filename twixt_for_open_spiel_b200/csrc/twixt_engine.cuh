@@ -153,6 +153,10 @@ struct LocalStack {
   TW_HD void push_if(bool c, uint32_t e) {
     if (c) push(e);
   }
+  // the (up to) four entries a flood visit discovers; a stack may test for room once for all four
+  TW_HD void push4_if(const bool c[4], const uint32_t e[4]) {
+    for (int i = 0; i < 4; ++i) push_if(c[i], e[i]);
+  }
   TW_HD uint32_t top() const { return v[sp - 1]; }
   TW_HD void pop() { --sp; }
   // pop the top entry, or take `otherwise` if there is none
@@ -308,10 +312,10 @@ TW_HD void flood_visit_entry(B& b, int flag_plane, Stack& stk, uint32_t e) {
   b.st_if(n_e2 != 0u, flag_plane, cx + 2, f_e2 | n_e2);
   b.st_if(n_w1 != 0u, flag_plane, cx - 1, f_w1 | n_w1);
   b.st_if(n_w2 != 0u, flag_plane, cx - 2, f_w2 | n_w2);
-  stk.push_if(n_e1 != 0u, flood_entry(cx + 1, n_e1));
-  stk.push_if(n_e2 != 0u, flood_entry(cx + 2, n_e2));
-  stk.push_if(n_w1 != 0u, flood_entry(cx - 1, n_w1));
-  stk.push_if(n_w2 != 0u, flood_entry(cx - 2, n_w2));
+  const bool found[4] = {n_e1 != 0u, n_e2 != 0u, n_w1 != 0u, n_w2 != 0u};
+  const uint32_t entries[4] = {flood_entry(cx + 1, n_e1), flood_entry(cx + 2, n_e2), flood_entry(cx - 1, n_w1),
+                               flood_entry(cx - 2, n_w2)};
+  stk.push4_if(found, entries);
 }
 
 // ... of the entry on top of the stack

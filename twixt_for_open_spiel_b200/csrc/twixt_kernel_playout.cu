@@ -61,9 +61,7 @@ constexpr int kStackWords = TW_PLAYOUT_STACK_WORDS;  // flood stack entries (one
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
-// + 1 word per lane that absorbs the flood-stack pushes of lanes whose condition is false (push_if): a
-// select of the address is cheaper than eight divergent branches per flood visit (41.8 -> 38.3 ms)
-__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords + 1; }
+__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
 
 // The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
 template <int NT>
@@ -83,10 +81,9 @@ struct PlayoutRef {
   __device__ __forceinline__ uint32_t ld_any(int plane, int col) const { return ld(plane, col); }
   // record word (after the header) -> shared-memory word
   __device__ __forceinline__ int smem_word(int w) const { return w < n() ? w + n() : (w < 2 * n() ? w - n() : w); }
-  __device__ __forceinline__ uint32_t* sink() const { return p + (kSmemPlanes * n() + kStackWords + kCacheWords) * 32; }
   // conditional plane store as ONE predicated st.shared: the compiler turns `if (c) st(...)` into a
   // BSSY/BRA/BSYNC region (ten of them per move showed up as branch_resolving stalls), and redirecting
-  // the store of the "false" lanes to a sink word measured slower than that
+  // the store of the "false" lanes to a spare word measured slower than that
   __device__ __forceinline__ void st_if(bool c, int plane, int col, uint32_t v) {
     const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p + (plane * n() + col) * 32));
     asm volatile(
@@ -136,29 +133,49 @@ struct PlayoutRef {
   }
 };
 
+// The flood stack in the lane's shared-memory column.  The stack pointer is kept as a shared-space byte
+// address (no index -> address arithmetic per access), pushes are predicated stores (inline PTX: the
+// compiler would make a branch region of each), and the room test is made once per visit for all four
+// possible pushes: if four entries might not fit, none is pushed and the visit counts as overflowed (the
+// closure pass recovers whatever was dropped).
 struct SmemStack {
-  uint32_t* base;  // smem, this lane's column of the stack words
-  int sp;
+  uint32_t* base;      // generic pointer to the lane's first stack word (the header is parked here while loading)
+  uint32_t base_addr;  // ... as a shared-space address
+  uint32_t top_addr;   // address one entry past the top; entries are 32 words = 128 bytes apart
   bool overflow;
-  __device__ __forceinline__ bool empty() const { return sp == 0; }
-  uint32_t* sink;  // the lane's sink word: where a refused entry is written
-  // branch-free conditional push
-  __device__ __forceinline__ void push_if(bool c, uint32_t cell) {
-    const bool room = sp < kStackWords;
-    const bool doit = c && room;
-    uint32_t* dst = doit ? base + sp * 32 : sink;
-    *dst = cell;
-    sp += doit ? 1 : 0;
-    overflow |= c && !room;
+  __device__ __forceinline__ void init(uint32_t* first_word) {
+    base = first_word;
+    base_addr = static_cast<uint32_t>(__cvta_generic_to_shared(first_word));
+    top_addr = base_addr;
+    overflow = false;
+  }
+  __device__ __forceinline__ void reset() {
+    top_addr = base_addr;
+    overflow = false;
+  }
+  __device__ __forceinline__ bool empty() const { return top_addr == base_addr; }
+  __device__ __forceinline__ void push4_if(const bool c[4], const uint32_t e[4]) {
+    const bool room = top_addr <= base_addr + (kStackWords - 4) * 128u;
+    overflow |= !room && (c[0] || c[1] || c[2] || c[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool doit = c[i] && room;
+      asm volatile(
+          "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp st.shared.u32 [%1], %2;\n\t}"
+          :: "r"(static_cast<uint32_t>(doit)), "r"(top_addr), "r"(e[i]) : "memory");
+      top_addr += doit ? 128u : 0u;
+    }
   }
   // pop the top entry, or take `otherwise` if there is none (branch-free: the load address is clamped)
   __device__ __forceinline__ uint32_t top_or(uint32_t otherwise) {
-    const bool have = sp > 0;
-    const uint32_t t = base[(have ? sp - 1 : 0) * 32];
-    sp -= have ? 1 : 0;
+    const bool have = top_addr != base_addr;
+    top_addr -= have ? 128u : 0u;
+    uint32_t t;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(top_addr) : "memory");
     return have ? t : otherwise;
   }
 };
+static_assert(kStackWords >= 4, "a flood visit pushes up to four entries");
 
 // resident blocks per SM the register allocation should allow: what shared memory allows for that size
 __host__ __device__ constexpr int playout_min_blocks(int nt) {
@@ -190,7 +207,8 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
   b.n_rt = n;
 #pragma unroll
   for (int i = 0; i < kCacheWords; ++i) b.cw[i] = 0u;
-  SmemStack stk{mine + kSmemPlanes * n * 32, 0, false, b.sink()};
+  SmemStack stk;
+  stk.init(mine + kSmemPlanes * n * 32);
   uint32_t s_lo = 0, s_hi = 0;
   // Random words: block `rq` (moves 4rq..4rq+3) in ra[], block rq+1 in rb[].  Lanes of a warp are at
   // different move numbers, so blocks are produced on a warp-uniform schedule (every 4th iteration, all
@@ -232,8 +250,7 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
     loading = true;
     playing = false;
     pend = 0;
-    stk.sp = 0;
-    stk.overflow = false;
+    stk.reset();
   };
   auto finish_take = [&]() {
     __pipeline_wait_prior(0);
