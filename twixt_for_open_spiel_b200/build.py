@@ -16,7 +16,9 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB = os.path.join(PKG, "libtwixt_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
-SOURCES = ["twixt_kernels_api.cu", "twixt_kernel_playout.cu", "twixt_batch.cu"]
+# (source, extra flags, object): the playout kernel is compiled once per size group (see its last section)
+SOURCES = [("twixt_kernels_api.cu", [], "twixt_kernels_api.o"), ("twixt_batch.cu", [], "twixt_batch.o")] + [
+    ("twixt_kernel_playout.cu", ["-DTW_PLAYOUT_GROUP=%d" % g], "twixt_kernel_playout_g%d.o" % g) for g in range(5)]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
@@ -62,9 +64,11 @@ def build(force: bool = False, verbose: bool = False, out: str = None, extra_fla
     nvcc = _nvcc()
     os.makedirs(obj_dir, exist_ok=True)
 
-    def compile_one(src: str) -> str:
-        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job) -> str:
+        src, flags, obj_name = job
+        obj = os.path.join(obj_dir, obj_name)
+        cmd = [nvcc, *NVCC_FLAGS, *flags, *extra_flags, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src),
+               "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
@@ -72,7 +76,7 @@ def build(force: bool = False, verbose: bool = False, out: str = None, extra_fla
             print(res.stdout, res.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", lib, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -38,6 +38,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "twixt_b200.h"
 #include "twixt_engine.cuh"
 #include "twixt_kernels.cuh"
 #include "twixt_philox.cuh"
@@ -465,24 +466,37 @@ cudaError_t launch_traced_or_not(const PlayoutArgs& a, cudaStream_t s) {
 
 }  // namespace
 
-cudaError_t playout_setup() {
+// This file is compiled once per size GROUP (-DTW_PLAYOUT_GROUP=g, g = 0..4; build.py runs the five
+// compilations in parallel): group g holds the kernels specialised for the board sizes 5+g, 10+g, 15+g and
+// 20+g, so every board size 5..24 runs with its size fixed at compile time (the run-time-size form of the
+// same kernel was 1.3x slower).  twixt_kernels_api.cu dispatches on (n - 5) % 5.
+#ifndef TW_PLAYOUT_GROUP
+#error "compile with -DTW_PLAYOUT_GROUP=0..4"
+#endif
+#define TW_CAT2(a, b) a##b
+#define TW_CAT(a, b) TW_CAT2(a, b)
+constexpr int kGroup = TW_PLAYOUT_GROUP;
+static_assert(kGroup >= 0 && kGroup < 5 && TWIXT_MIN_BOARD_SIZE == 5 && TWIXT_MAX_BOARD_SIZE == 24, "size groups");
+
+cudaError_t TW_CAT(playout_setup_g, TW_PLAYOUT_GROUP)() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if ((e = setup_nt<0>(24)) != cudaSuccess) return e;
-  if ((e = setup_nt<8>(8)) != cudaSuccess) return e;
-  if ((e = setup_nt<12>(12)) != cudaSuccess) return e;
-  return setup_nt<24>(24);
+  if ((e = setup_nt<5 + kGroup>(5 + kGroup)) != cudaSuccess) return e;
+  if ((e = setup_nt<10 + kGroup>(10 + kGroup)) != cudaSuccess) return e;
+  if ((e = setup_nt<15 + kGroup>(15 + kGroup)) != cudaSuccess) return e;
+  return setup_nt<20 + kGroup>(20 + kGroup);
 }
 
-cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s) {
+cudaError_t TW_CAT(launch_playout_g, TW_PLAYOUT_GROUP)(const PlayoutArgs& a, cudaStream_t s) {
   if (a.count <= 0) return cudaSuccess;
   switch (a.n) {
-    case 8: return launch_traced_or_not<8>(a, s);
-    case 12: return launch_traced_or_not<12>(a, s);
-    case 24: return launch_traced_or_not<24>(a, s);
-    default: return launch_traced_or_not<0>(a, s);
+    case 5 + kGroup: return launch_traced_or_not<5 + kGroup>(a, s);
+    case 10 + kGroup: return launch_traced_or_not<10 + kGroup>(a, s);
+    case 15 + kGroup: return launch_traced_or_not<15 + kGroup>(a, s);
+    case 20 + kGroup: return launch_traced_or_not<20 + kGroup>(a, s);
+    default: return cudaErrorInvalidValue;
   }
 }
 

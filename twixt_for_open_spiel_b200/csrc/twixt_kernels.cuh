@@ -54,5 +54,16 @@ cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, fl
 cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s);
 // one-time per-process setup of the playout kernels (opt-in shared memory)
 cudaError_t playout_setup();
+// the five size groups of twixt_kernel_playout.cu (board sizes 5+g, 10+g, 15+g, 20+g)
+cudaError_t playout_setup_g0();
+cudaError_t playout_setup_g1();
+cudaError_t playout_setup_g2();
+cudaError_t playout_setup_g3();
+cudaError_t playout_setup_g4();
+cudaError_t launch_playout_g0(const PlayoutArgs& a, cudaStream_t s);
+cudaError_t launch_playout_g1(const PlayoutArgs& a, cudaStream_t s);
+cudaError_t launch_playout_g2(const PlayoutArgs& a, cudaStream_t s);
+cudaError_t launch_playout_g3(const PlayoutArgs& a, cudaStream_t s);
+cudaError_t launch_playout_g4(const PlayoutArgs& a, cudaStream_t s);
 
 }  // namespace twixt

@@ -507,4 +507,25 @@ cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, fl
   return cudaGetLastError();
 }
 
+// The fused playout kernel: one compiled form per board size, in five translation units (size groups).
+cudaError_t playout_setup() {
+  cudaError_t e;
+  if ((e = playout_setup_g0()) != cudaSuccess) return e;
+  if ((e = playout_setup_g1()) != cudaSuccess) return e;
+  if ((e = playout_setup_g2()) != cudaSuccess) return e;
+  if ((e = playout_setup_g3()) != cudaSuccess) return e;
+  return playout_setup_g4();
+}
+
+cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s) {
+  if (a.n < TWIXT_MIN_BOARD_SIZE || a.n > TWIXT_MAX_BOARD_SIZE) return cudaErrorInvalidValue;
+  switch ((a.n - TWIXT_MIN_BOARD_SIZE) % 5) {
+    case 0: return launch_playout_g0(a, s);
+    case 1: return launch_playout_g1(a, s);
+    case 2: return launch_playout_g2(a, s);
+    case 3: return launch_playout_g3(a, s);
+    default: return launch_playout_g4(a, s);
+  }
+}
+
 }  // namespace twixt
