@@ -69,6 +69,9 @@ template <int NT>
 struct PlayoutRef {
   uint32_t* p;     // smem, this lane's column
   uint32_t* gblk;  // global: the record's P_BLOCKED words
+  // NT is the board size (every size 5..24 is instantiated, see the end of the file).  The run-time-size
+  // form (NT == 0, n_rt, count cache in shared memory) is no longer instantiated; it is kept because taking
+  // it out changed ptxas' schedule of the n = 24 kernel for the worse (18.4 -> 18.8 ms, measured twice).
   int n_rt;
   __device__ __forceinline__ int n() const { return NT > 0 ? NT : n_rt; }
   // Shared-memory order of the planes: BLUE, RED, the four link planes, START, END (the record has RED
