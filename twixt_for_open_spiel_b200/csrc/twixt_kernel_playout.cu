@@ -19,17 +19,25 @@
 //    one MOVE for the lanes without flood work and one flood VISIT for the
 //    lanes with it, instead of 31 lanes idling through one lane's whole flood;
 //    the flood stack lives in shared memory next to the planes;
-//  * candidate links are handled direction-major and branch-free (place_peg);
+//  * candidate links are handled direction-major and branch-free (link_move),
+//    a flood visit handles a whole stack entry (all its cells of one column);
 //  * lanes are PERSISTENT: games end at different plies (250..573 at n=24), so
 //    a lane whose game is over writes its env back and takes the next env of
 //    the range from a ticket counter instead of idling until the slowest game
 //    of its warp ends; the new env arrives by cp.async (LDGSTS) while the rest
 //    of the warp keeps playing.
-// Shared memory per env: planes 0..7 (pegs, links, border flags) + the flood
-// stack + a per-column count cache that replaces the 24-word legal scan by 6
-// bytewise words (twixt_engine.cuh, count_cache_*).  The "blocked neighbour"
-// plane is write-only for the rules, so it stays in HBM and is OR-ed in place
-// (RED.OR, fire-and-forget) on a blocked link.
+// Control structure (profiles/r1_playout_v15_* -> v18_*): with two warps per
+// scheduler every reconvergence point shows up as a stall, so an iteration has
+// exactly three data-dependent branch regions -- RARE (finish a load, retire
+// an env and take the next, first half of a swap), MOVE, FLOOD -- plus the
+// warp-uniform Philox refresh / loop-exit vote every fourth iteration.
+// Shared memory per env: the planes BLUE, RED, links x4, START, END (this
+// order puts an always-zero word in front of every link plane, so the link
+// window of a move is loaded without bounds tests) + the flood stack; the
+// per-column count cache that replaces the 24-word legal scan by 6 bytewise
+// words (twixt_engine.cuh, count_cache_*) lives in registers.  The "blocked
+// neighbour" plane is write-only for the rules, so it stays in HBM and is
+// OR-ed in place (RED.OR, fire-and-forget).
 //
 // Reference loop reproduced: upstream example.cc / RandomRolloutEvaluator
 // (LegalActions -> uniform pick -> ApplyAction until IsTerminal), with the
