@@ -39,13 +39,6 @@ __device__ __forceinline__ uint32_t ldg32(const uint32_t* p) {
   return v;
 }
 
-// 16-byte store of OUTPUT data (lists, masks, tensors): written once, never read back by these kernels
-#ifdef TW_STREAM_STORES
-#define TW_STORE16(ptr, val) __stcs((ptr), (val))
-#else
-#define TW_STORE16(ptr, val) (*(ptr) = (val))
-#endif
-
 // ---------------------------------------------------------------- reset ---
 // Board::Board (twixtboard.cc:168-174): empty board, both legal lists full.
 __global__ void reset_kernel(uint32_t* __restrict__ records, int64_t count, int n, int quads_per_record) {
@@ -198,7 +191,7 @@ __global__ void __launch_bounds__(kLegalWarps * 32, 6) legal_actions_kernel(
         const int nvec = total / kPerVec;
 #pragma unroll 1
         for (int v = lane; v < nvec; v += 32)
-          TW_STORE16(reinterpret_cast<uint4*>(dst) + v, widen_actions<T>(row, v));
+          reinterpret_cast<uint4*>(dst)[v] = widen_actions<T>(row, v);
         const int i = nvec * kPerVec + lane;  // fewer than kPerVec <= 8 entries are left
         if (i < total) dst[i] = static_cast<T>(row[i]);
       } else {
@@ -245,7 +238,7 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_mask_kernel(const uint
 #pragma unroll
       for (int v = 0; v < (kVecs + 31) / 32; ++v)
         if (v * 32 + lane < kVecs)
-          TW_STORE16(reinterpret_cast<uint4*>(dst) + v * 32 + lane, reinterpret_cast<const uint4*>(row)[v * 32 + lane]);
+          reinterpret_cast<uint4*>(dst)[v * 32 + lane] = reinterpret_cast<const uint4*>(row)[v * 32 + lane];
       __syncwarp();
     } else {
       for (int base = 0; base < cells; base += 32) {
@@ -392,7 +385,7 @@ __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t
         v.y = (b4 & 2u) ? 1.0f : 0.0f;
         v.z = (b4 & 4u) ? 1.0f : 0.0f;
         v.w = (b4 & 8u) ? 1.0f : 0.0f;
-        TW_STORE16(reinterpret_cast<float4*>(dst) + q, v);
+        reinterpret_cast<float4*>(dst)[q] = v;
       }
     } else {
       for (int j = tid; j < total; j += kObsThreads) dst[j] = ((stream[j >> 5] >> (j & 31)) & 1u) ? 1.0f : 0.0f;
