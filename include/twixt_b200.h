@@ -99,6 +99,8 @@ typedef struct twixt_stats {
   int64_t swaps;      /* playouts in which the swap rule was used */
   int64_t max_length; /* longest finished game (plies) */
   int64_t kernel_launches; /* kernels launched by this batch since creation */
+  int64_t debug_violations; /* always 0 in the product build; the bounds-instrumented test variant of the
+                               playout kernel counts accesses outside an env's own storage here */
 } twixt_stats;
 
 const char* twixt_last_error(void);
@@ -132,7 +134,9 @@ int twixt_reset(twixt_batch* b, int64_t first, int64_t count);
 
 /* State::Clone(), twixt.h:80-82.  dst env i <- src env i (ranges may not
  * overlap), or dst env first+i <- env src_ids[i] for the gather form
- * (src_ids: int64, host or device). */
+ * (src_ids: int64, host or device).  Every id must lie in [0, num_envs) and outside the destination range;
+ * an offending id copies nothing for its env and fails the call with TWIXT_EINVAL (ids on the device are
+ * checked by the kernel itself).  twixt_clone_from rejects overlapping ranges within one batch. */
 int twixt_clone(twixt_batch* b, int64_t src_first, int64_t dst_first, int64_t count);
 int twixt_clone_gather(twixt_batch* b, const int64_t* src_ids, int64_t dst_first, int64_t count);
 /* Clone between two batches of the same board size (possibly on one device). */
@@ -170,6 +174,24 @@ int twixt_returns(twixt_batch* b, int64_t first, int64_t count, float* out);
  * float32, zero-filled then 1.0s; identical for both players. */
 int twixt_observation(twixt_batch* b, int64_t first, int64_t count, float* out);
 
+/* ObservationTensor + LegalActionsMask of the same envs in ONE pass over the records (the producer of an
+ * AlphaZero-style inference batch, BASELINE config C5): out_obs as twixt_observation, out_mask as
+ * twixt_legal_mask; bit-identical to the two separate calls. */
+int twixt_observation_and_mask(twixt_batch* b, int64_t first, int64_t count, float* out_obs,
+                               uint8_t* out_mask);
+
+/* Replays a whole action history per env in one launch: upstream serialises a state as its action history
+ * (State::Serialize) and Game::DeserializeState re-applies it move by move; the reference has no UndoAction
+ * (twixt.h:84), so replay is also how a search returns to an earlier position.  actions is [count, stride]
+ * int32; env first+i applies actions[i*stride + k] for k = 0 .. len_i-1 from its CURRENT state, with the
+ * legality test of DoApplyAction (twixt.h:93-104) before every move, where len_i = lengths[i] (nullable:
+ * then a row ends at its first negative entry or at stride).  An env stops at its first illegal action,
+ * keeping the state reached; out_applied (nullable) is [count] int32 = moves made.  Returns TWIXT_EILLEGAL
+ * with the reference's message for the lowest such env (only checked when out_applied is null or any
+ * pointer is a host pointer; with device pointers throughout the call is asynchronous). */
+int twixt_replay(twixt_batch* b, int64_t first, int64_t count, const int32_t* actions, int64_t stride,
+                 const int32_t* lengths, int32_t* out_applied);
+
 /* The random-playout loop of upstream example.cc / RandomRolloutEvaluator
  * (LegalActions -> uniform pick -> ApplyAction until IsTerminal), fused into
  * one kernel with the env state held on chip.  Every env in the range is
@@ -186,12 +208,29 @@ int twixt_playout(twixt_batch* b, int64_t first, int64_t count, int32_t max_plie
                   const uint64_t* stream_ids, float* out_returns, int32_t* out_lengths,
                   uint16_t* out_actions, int32_t trace_plies);
 
-/* Raw state records, [count, record_words] uint32 (host or device). */
+/* Raw state records, [count, record_words] uint32 (host or device).
+ * The reference can only reach a state through DoApplyAction (twixt.h:93-104); records handed to
+ * twixt_import_state are therefore VALIDATED on the device before any env is overwritten (header ranges,
+ * peg placement and counts, link endpoints, flag/blocked bits on pegs only, recounted legal-cell counters,
+ * zero padding).  A bad record fails the whole call with TWIXT_EINVAL, "invalid state record at index I:
+ * <reason>", and leaves the batch untouched.  twixt_set_validation(b, 0) skips the check for trusted
+ * records (a plain copy, asynchronous for device pointers); the default is on. */
 int twixt_export_state(twixt_batch* b, int64_t first, int64_t count, uint32_t* out_records);
 int twixt_import_state(twixt_batch* b, int64_t first, int64_t count, const uint32_t* records);
+int twixt_set_validation(twixt_batch* b, int enabled);
 
 int twixt_get_stats(twixt_batch* b, twixt_stats* out);
 int twixt_stats_reset(twixt_batch* b);
+
+/* Multi-GPU plumbing for hosts that are not Python (envs shard by contiguous global id ranges,
+ * no data-path collective, one reduction of the counters).  twixt_shard_range: rank's share [first,
+ * first+count) of global_envs envs over `world` ranks (shares differ by at most one env); create the rank's
+ * batch with `count` envs and call twixt_set_stream_base(b, first) so games do not depend on the GPU
+ * count.  twixt_stats_accumulate: acc += part (sums; max for max_length) -- apply it to the ranks'
+ * twixt_get_stats results, or to the output of an MPI/NCCL all-gather.  Neither needs a GPU. */
+int twixt_shard_range(int64_t global_envs, int32_t world, int32_t rank, int64_t* out_first,
+                      int64_t* out_count);
+int twixt_stats_accumulate(twixt_stats* acc, const twixt_stats* part);
 
 #ifdef __cplusplus
 }

@@ -390,6 +390,36 @@ class RefState(_StateBase):
         a = np.asarray(actions, dtype=np.int64)
         return self.lib.ref_replay(self.h, _ptr(a), len(a))
 
+    def export_record(self) -> np.ndarray:
+        """The packed state record (include/twixt_b200.h) of the REFERENCE's board, assembled here from its
+        cell internals (ref_export_cells) and header -- the same mapping as oracle_export_record in
+        twixt_oracle.c -- so a CUDA record can be compared with the compiled reference directly."""
+        n = self.n
+        cells = self.export_cells().reshape(n, n, 4).astype(np.int64)  # [x, y, field]
+        hdr = self.board_header()  # move_counter, swapped, result, move_one x, y
+        words = (4 + 9 * n + 3) // 4 * 4
+        rec = np.zeros(words, dtype=np.uint32)
+        color, links, blocked, flags = (cells[:, :, k] for k in range(4))
+        bit = (np.int64(1) << np.arange(n, dtype=np.int64))[None, :]  # bit y of a column word
+
+        def column_words(sel):  # [x, y] bool -> [x] uint32
+            return (sel * bit).sum(axis=1).astype(np.uint32)
+
+        peg = color < 2
+        own = np.where(peg, color, 0)
+        planes = [column_words(color == 0), column_words(color == 1)]
+        planes += [column_words(peg & (((links >> d) & 1) == 1)) for d in range(4)]
+        planes.append(column_words(peg & (((flags >> (2 * own)) & 1) == 1)))      # owner's start line
+        planes.append(column_words(peg & (((flags >> (2 * own + 1)) & 1) == 1)))  # owner's end line
+        planes.append(column_words(peg & ((blocked & 15) != 0)))
+        rec[4:4 + 9 * n] = np.concatenate(planes)
+        empty = color == 2  # corners are 3 (off-board)
+        rec[0] = hdr[0]
+        rec[1] = hdr[2] | (hdr[1] << 2)
+        rec[2] = 0xFFFFFFFF if hdr[0] == 0 else hdr[3] * n + hdr[4]
+        rec[3] = int(empty[1:n - 1, :].sum()) | (int(empty[:, 1:n - 1].sum()) << 16)
+        return rec
+
     def playout_philox(self, seed: int, stream: int, max_plies: int = 1 << 30) -> List[int]:
         out = np.zeros(self.n * self.n, dtype=np.int64)
         c = self.lib.ref_playout_philox(self.h, seed, stream, max_plies, _ptr(out))

@@ -2,6 +2,8 @@
 // assertions of the reference's twixt_test.cc:50-199 on TwixTB200Game / TwixTB200State, compiled against
 // the open_spiel header shim.  `adapter_driver cpu` runs what needs no GPU (parameter errors, renderer);
 // `adapter_driver gpu` runs the state tests on cuda:0.
+#include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -158,14 +160,110 @@ static int DrawTest() {  // twixt_test.cc:185-199
   return 0;
 }
 
+// CRC-32 (IEEE, as zlib.crc32) of a byte string
+static uint32_t Crc32(const std::string& s) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (unsigned char ch : s) {
+    c ^= ch;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+  }
+  return c ^ 0xFFFFFFFFu;
+}
+
+// ToString() of the adapter at EVERY ply of reference-generated games (tests/golden/ref_strings.json, written
+// out by the test as plain text): the CRC of the picture at every ply, the full text at the plies the
+// fixture keeps.  The games hold links of all eight directions in both colours, the swap, both wins and a
+// draw, with and without ANSI colour codes -- so RenderRecord (and the record it is fed by the CUDA path)
+// is compared with Board::ToString (twixtboard.cc:278-448) beyond the empty board.
+static int StringsTest(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  EXPECT(f != nullptr);
+  int games = 0;
+  char tag[16];
+  while (std::fscanf(f, "%15s", tag) == 1 && std::string(tag) == "GAME") {
+    int n = 0, ansi = 0, num = 0;
+    EXPECT(std::fscanf(f, "%d %d %d", &n, &ansi, &num) == 3);
+    std::vector<long long> actions(static_cast<size_t>(num));
+    for (auto& a : actions) EXPECT(std::fscanf(f, "%lld", &a) == 1);
+    std::vector<uint32_t> crcs(static_cast<size_t>(num) + 1);
+    for (auto& c : crcs) EXPECT(std::fscanf(f, "%u", &c) == 1);
+    int kept = 0;
+    EXPECT(std::fscanf(f, "%d", &kept) == 1);
+    std::vector<std::pair<int, std::string>> texts;
+    for (int k = 0; k < kept; ++k) {
+      int ply = 0;
+      long bytes = 0;
+      EXPECT(std::fscanf(f, "%d %ld", &ply, &bytes) == 2);
+      EXPECT(std::fgetc(f) == '\n');
+      std::string t(static_cast<size_t>(bytes), '\0');
+      EXPECT(std::fread(&t[0], 1, t.size(), f) == t.size());
+      texts.emplace_back(ply, std::move(t));
+    }
+    GameParameters params;
+    params.insert({"board_size", GameParameter(n, false)});
+    params.insert({"ansi_color_output", GameParameter(ansi != 0, false)});
+    std::shared_ptr<const open_spiel::Game> game(new TwixTB200Game(params));
+    auto state = game->NewInitialState();
+    size_t next_text = 0;
+    for (int ply = 0; ply <= num; ++ply) {
+      const std::string got = state->ToString();
+      if (Crc32(got) != crcs[static_cast<size_t>(ply)]) {
+        std::fprintf(stderr, "ToString differs: game %d n=%d ansi=%d ply %d\n", games, n, ansi, ply);
+        return 1;
+      }
+      if (next_text < texts.size() && texts[next_text].first == ply) {
+        EXPECT(got == texts[next_text].second);
+        EXPECT(state->ObservationString(0) == got && state->InformationStateString(1) == got);  // twixt.h:65-75
+        ++next_text;
+      }
+      if (ply < num) state->ApplyAction(actions[static_cast<size_t>(ply)]);
+    }
+    EXPECT(next_text == texts.size());
+    EXPECT(state->IsTerminal());
+    ++games;
+  }
+  std::fclose(f);
+  EXPECT(games >= 10);
+  return 0;
+}
+
+// RenderRecord alone (no GPU): records written by the test from the oracle at plies of the reference-generated
+// string fixture, each with the reference's picture of that position.
+static int RenderRecordsTest(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  EXPECT(f != nullptr);
+  int seen = 0;
+  char tag[16];
+  while (std::fscanf(f, "%15s", tag) == 1 && std::string(tag) == "REC") {
+    int n = 0, ansi = 0, words = 0;
+    long bytes = 0;
+    EXPECT(std::fscanf(f, "%d %d %d %ld", &n, &ansi, &words, &bytes) == 4);
+    std::vector<uint32_t> rec(static_cast<size_t>(words));
+    for (auto& w : rec) EXPECT(std::fscanf(f, "%u", &w) == 1);
+    EXPECT(std::fgetc(f) == '\n');
+    std::string want(static_cast<size_t>(bytes), '\0');
+    EXPECT(std::fread(&want[0], 1, want.size(), f) == want.size());
+    if (open_spiel::twixt_b200::RenderRecord(rec.data(), n, ansi != 0) != want) {
+      std::fprintf(stderr, "RenderRecord differs: record %d (n=%d ansi=%d)\n", seen, n, ansi);
+      return 1;
+    }
+    ++seen;
+  }
+  std::fclose(f);
+  EXPECT(seen >= 50);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
   try {
     if (mode == "cpu") {
       if (ParameterTest() != 0) return 1;
       if (argc > 2 && RenderTest(argv[2]) != 0) return 1;
+      if (argc > 3 && RenderRecordsTest(argv[3]) != 0) return 1;
     } else {
       if (SwapTest() != 0 || LegalActionsTest() != 0 || DrawTest() != 0) return 1;
+      if (argc > 2 && StringsTest(argv[2]) != 0) return 1;
     }
   } catch (const std::exception& e) {
     std::fprintf(stderr, "unexpected exception: %s\n", e.what());

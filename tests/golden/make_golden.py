@@ -12,6 +12,10 @@ Needs /root/reference (authoring container only):
         per ply the current player, the CRC32 of the int64 legal list and of the
         float32 observation tensor, plus terminal flag / returns at the end and a
         few complete dumps;
+  * ref_strings.json      Board::ToString (twixtboard.cc:278-448) of the compiled reference at EVERY ply of
+        the swap, win and draw games of twixt_test.cc and of seeded random games at n = 6, 12, 24 chosen so
+        that links of all eight compass directions, both colours, `[swapped]`, `[x has won]`, `[o has won]`
+        and `[draw]` occur; with and without ANSI colour codes;
   * kats.json             the known-answer tests of twixt_test.cc restated as data,
         and the Random123 Philox4x32-10 known answers.
 The tests never read /root/reference; they read these files.
@@ -137,6 +141,62 @@ def gen_games():
     return games
 
 
+def ref_strings(n, actions, ansi):
+    rg = pyoracle.RefGame(n, ansi)
+    st = rg.new_initial_state()
+    all_strings, dirs = [st.to_string()], 0
+    for a in actions:
+        st.apply_action(a)
+        all_strings.append(st.to_string())
+    for c in st.export_cells():
+        dirs |= int(c[1])
+    # the CRC32 of the UTF-8 picture at EVERY ply; the text itself at every ply of a short game, at a few
+    # plies (first, last, some in between) of a long one -- keeps the fixture small
+    last = len(actions)
+    keep = range(last + 1) if last <= 40 else sorted({0, 1, 2, last // 3, 2 * last // 3, last - 1, last})
+    res = {"n": n, "ansi": ansi, "actions": list(actions), "strings": {str(k): all_strings[k] for k in keep},
+           "crcs": [zlib.crc32(t.encode("utf-8")) & 0xFFFFFFFF for t in all_strings], "link_directions": dirs,
+           "returns": st.returns()}
+    del st
+    del rg
+    return res
+
+
+def gen_strings():
+    from helpers import draw_seeking_actions, random_game_actions
+    games = []
+    og5 = pyoracle.OracleGame(5)
+    fixed = [(8, [19, 19, 36]), (8, [21, 38, 15, 11, 27, 17, 42, 45, 48]), (5, draw_seeking_actions(og5, (0, 1)))]
+    for n, acts in fixed:
+        for ansi in (True, False):
+            games.append(ref_strings(n, acts, ansi))
+    # seeded random games: keep looking until a red win, a blue win and a swapped game are in the set
+    for n, ansi in ((6, True), (12, False), (24, True)):
+        og = pyoracle.OracleGame(n)
+        rng = random.Random(77 + n)
+        want = {"red", "blue", "swap"}
+        for i in range(400):
+            if not want:
+                break
+            acts = random_game_actions(og, rng, force_swap=(i % 2 == 1))
+            st = og.new_initial_state()
+            st.replay(acts)
+            tag = "red" if st.returns()[0] > 0 else ("blue" if st.returns()[1] > 0 else None)
+            swapped = len(acts) > 1 and acts[0] == acts[1]
+            hit = ({tag} if tag else set()) | ({"swap"} if swapped else set())
+            if hit & want:
+                want -= hit
+                games.append(ref_strings(n, acts, ansi))
+    all_dirs = 0
+    for g in games:
+        all_dirs |= g["link_directions"]
+    assert all_dirs == 0xFF, all_dirs
+    tails = "".join(g["strings"][str(len(g["actions"]))][-24:] for g in games)
+    for needle in ("[swapped]", "[x has won]", "[o has won]", "[draw]"):
+        assert needle in tails, needle
+    return games
+
+
 def main():
     assert os.path.exists(PLAYTHROUGH), "needs /root/reference"
     pt = parse_playthrough(PLAYTHROUGH)
@@ -179,7 +239,10 @@ def main():
     }
     with open(os.path.join(HERE, "kats.json"), "w") as f:
         json.dump(kats, f, indent=1)
-    for name in ("playthrough_n8.json", "ref_games.json", "kats.json"):
+    with open(os.path.join(HERE, "ref_strings.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py on oracle/_ref (unmodified reference)",
+                   "games": gen_strings()}, f)
+    for name in ("playthrough_n8.json", "ref_games.json", "ref_strings.json", "kats.json"):
         print(name, os.path.getsize(os.path.join(HERE, name)))
 
 

@@ -28,16 +28,58 @@ def driver():
     return EXE
 
 
-def test_adapter_parameters_and_renderer(driver, tmp_path):
+def test_adapter_parameters_and_renderer(driver, tmp_path, oracle_mod):
+    """Parameter errors; the C++ renderer on the empty board AND on every kept position of the
+    reference-generated string fixture (records from the oracle: links of all eight directions, both
+    colours, swap / win / draw suffixes, ANSI on and off)."""
     with open(os.path.join(HERE, "golden", "playthrough_n8.json")) as f:
         s0 = json.load(f)["states"][0]["observation_string"]
     want = tmp_path / "state0.txt"
     want.write_bytes(s0.encode("utf-8"))
-    res = subprocess.run([driver, "cpu", str(want)], capture_output=True, text=True)
+    with open(os.path.join(HERE, "golden", "ref_strings.json")) as f:
+        games = json.load(f)["games"]
+    recs = tmp_path / "records.txt"
+    with open(recs, "wb") as out:
+        for g in games:
+            og = oracle_mod.OracleGame(g["n"])
+            for ply in sorted(g["strings"], key=int):
+                st = og.new_initial_state()
+                st.replay(g["actions"][:int(ply)])
+                rec = st.export_record()
+                raw = g["strings"][ply].encode("utf-8")
+                out.write(("REC %d %d %d %d\n" % (g["n"], 1 if g["ansi"] else 0, len(rec), len(raw))).encode())
+                out.write((" ".join(str(int(w)) for w in rec) + "\n").encode())
+                out.write(raw)
+                out.write(b"\n")
+        out.write(b"END\n")
+    res = subprocess.run([driver, "cpu", str(want), str(recs)], capture_output=True, text=True)
     assert res.returncode == 0 and "OK" in res.stdout, res.stderr
 
 
+def write_strings_fixture(path):
+    """tests/golden/ref_strings.json as the plain-text file adapter_driver reads."""
+    with open(os.path.join(HERE, "golden", "ref_strings.json")) as f:
+        games = json.load(f)["games"]
+    with open(path, "wb") as out:
+        for g in games:
+            out.write(("GAME %d %d %d\n" % (g["n"], 1 if g["ansi"] else 0, len(g["actions"]))).encode())
+            out.write((" ".join(str(a) for a in g["actions"]) + "\n").encode())
+            out.write((" ".join(str(c) for c in g["crcs"]) + "\n").encode())
+            out.write(("%d\n" % len(g["strings"])).encode())
+            for ply in sorted(g["strings"], key=int):
+                raw = g["strings"][ply].encode("utf-8")
+                out.write(("%s %d\n" % (ply, len(raw))).encode())
+                out.write(raw)
+                out.write(b"\n")
+        out.write(b"END\n")
+    return len(games)
+
+
 @pytest.mark.gpu
-def test_adapter_reference_tests_on_gpu(driver):
-    res = subprocess.run([driver, "gpu"], capture_output=True, text=True)
+def test_adapter_reference_tests_on_gpu(driver, tmp_path):
+    """twixt_test.cc's state tests, then ToString at every ply of the reference-generated string fixture
+    (swap, both wins, draw, all eight link directions, ANSI on/off) through the C++ adapter on cuda:0."""
+    fixture = tmp_path / "ref_strings.txt"
+    assert write_strings_fixture(str(fixture)) >= 10
+    res = subprocess.run([driver, "gpu", str(fixture)], capture_output=True, text=True)
     assert res.returncode == 0 and "OK" in res.stdout, res.stderr

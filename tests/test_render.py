@@ -70,3 +70,24 @@ def test_action_to_string_matches_reference(oracle_mod, have_ref):
                 assert TwixTState.action_to_string(fake, p, a) == rs.action_to_string(p, a)
         fake._game = None
         del rs, rg
+
+
+def test_reference_generated_strings(oracle_mod):
+    """tests/golden/ref_strings.json (the compiled reference's ToString at every ply of swap / win / draw and
+    random games, all eight link directions, ANSI on and off) against the host renderer over oracle records."""
+    import zlib
+    from twixt_for_open_spiel_b200.render import board_to_string
+    with open(os.path.join(GOLDEN, "ref_strings.json")) as f:
+        games = json.load(f)["games"]
+    dirs = 0
+    for g in games:
+        st = oracle_mod.OracleGame(g["n"]).new_initial_state()
+        for ply in range(len(g["actions"]) + 1):
+            text = board_to_string(st.export_record(), g["n"], g["ansi"])
+            assert zlib.crc32(text.encode("utf-8")) & 0xFFFFFFFF == g["crcs"][ply], (g["n"], ply)
+            if str(ply) in g["strings"]:
+                assert text == g["strings"][str(ply)]
+            if ply < len(g["actions"]):
+                st.apply_action(g["actions"][ply])
+        dirs |= g["link_directions"]
+    assert dirs == 0xFF

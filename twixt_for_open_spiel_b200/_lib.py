@@ -39,6 +39,7 @@ class Stats(C.Structure):
         ("swaps", C.c_int64),
         ("max_length", C.c_int64),
         ("kernel_launches", C.c_int64),
+        ("debug_violations", C.c_int64),
     ]
 
 
@@ -69,9 +70,14 @@ SYMBOLS = [
     ("twixt_is_terminal", C.c_int, [_P, _I64, _I64, _P]),
     ("twixt_returns", C.c_int, [_P, _I64, _I64, _P]),
     ("twixt_observation", C.c_int, [_P, _I64, _I64, _P]),
+    ("twixt_observation_and_mask", C.c_int, [_P, _I64, _I64, _P, _P]),
+    ("twixt_replay", C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P]),
     ("twixt_playout", C.c_int, [_P, _I64, _I64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
     ("twixt_export_state", C.c_int, [_P, _I64, _I64, _P]),
     ("twixt_import_state", C.c_int, [_P, _I64, _I64, _P]),
+    ("twixt_set_validation", C.c_int, [_P, C.c_int]),
+    ("twixt_shard_range", C.c_int, [_I64, C.c_int32, C.c_int32, C.POINTER(_I64), C.POINTER(_I64)]),
+    ("twixt_stats_accumulate", C.c_int, [C.POINTER(Stats), C.POINTER(Stats)]),
     ("twixt_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("twixt_stats_reset", C.c_int, [_P]),
 ]
@@ -102,11 +108,11 @@ def load() -> C.CDLL:
         _build.build(force=True)
     elif _build.needs_build():
         try:
-            _build.build()
-        except Exception:
-            # stale-but-present library and no compiler (never the case in this image): use it
-            if not os.path.exists(_build.LIB):
-                raise
+            _build.nvcc_path()
+        except RuntimeError:
+            pass  # no compiler on this machine: the present library is all there is
+        else:
+            _build.build()  # a compile or link error in edited sources must surface, not hide behind a stale binary
     lib = C.CDLL(_build.LIB)
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete

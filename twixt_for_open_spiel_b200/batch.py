@@ -223,6 +223,42 @@ class TwixTBatch:
                                                 _ptr(out, _dt(np.float32, "float32"), count * self.info.obs_size)))
         return out
 
+    def observation_and_mask(self, first: int = 0, count: Optional[int] = None, out_obs=None, out_mask=None):
+        """ObservationTensor + LegalActionsMask in one pass over the records (twixt_observation_and_mask)."""
+        first, count = self._range(first, count)
+        if out_obs is None:
+            out_obs = np.empty((count,) + self.obs_shape, dtype=np.float32)
+        if out_mask is None:
+            out_mask = np.zeros((count, self.board_size * self.board_size), dtype=np.uint8)
+        self._check(self._lib.twixt_observation_and_mask(
+            self._h, first, count, _ptr(out_obs, _dt(np.float32, "float32"), count * self.info.obs_size),
+            _ptr(out_mask, _dt(np.uint8, "uint8"), count * self.board_size ** 2)))
+        return out_obs, out_mask
+
+    def replay(self, actions, first: int = 0, lengths=None, out_applied=None, raise_on_illegal: bool = True):
+        """Applies a whole action history per env in one launch (twixt_replay).
+
+        actions: [count, T] int32 (numpy or torch), rows padded with negative entries or cut by `lengths`.
+        Returns out_applied [count] int32 = moves made per env."""
+        if _is_torch(actions):
+            count, stride = int(actions.shape[0]), int(actions.shape[1])
+        else:
+            actions = np.ascontiguousarray(actions, dtype=np.int32)
+            if actions.ndim != 2:
+                raise ValueError("actions must be [count, T]")
+            count, stride = actions.shape
+        if lengths is not None and not _is_torch(lengths):
+            lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        if out_applied is None and not _is_torch(actions):
+            out_applied = np.zeros(count, dtype=np.int32)
+        rc = self._lib.twixt_replay(self._h, int(first), count, _ptr(actions, _dt(np.int32, "int32")), stride,
+                                    _ptr(lengths, _dt(np.int32, "int32"), count) if lengths is not None else 0,
+                                    _ptr(out_applied, _dt(np.int32, "int32"), count) if out_applied is not None else 0)
+        if rc == _lib.EILLEGAL and not raise_on_illegal:
+            return out_applied
+        self._check(rc)
+        return out_applied
+
     def playout(self, first: int = 0, count: Optional[int] = None, max_plies: Optional[int] = None, stream_ids=None,
                 out_returns=None, out_lengths=None, out_actions=None, want_returns: bool = True,
                 want_lengths: bool = True, trace: bool = False):
@@ -260,6 +296,10 @@ class TwixTBatch:
             out = np.zeros((count, self.record_words), dtype=np.uint32)
         self._check(self._lib.twixt_export_state(self._h, first, count, _ptr(out)))
         return out
+
+    def set_validation(self, enabled: bool):
+        """import_state validates records by default (twixt_import_state); off = trusted records."""
+        self._check(self._lib.twixt_set_validation(self._h, 1 if enabled else 0))
 
     def import_state(self, records, first: int = 0):
         if not _is_torch(records):

@@ -32,6 +32,10 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libtwixt_b200.so cannot be built")
 
 
+def nvcc_path() -> str:
+    return _nvcc()
+
+
 def _fingerprint() -> str:
     h = hashlib.sha256()
     names = sorted(os.listdir(CSRC)) + ["../../include/twixt_b200.h"]
@@ -63,6 +67,20 @@ def build(force: bool = False, verbose: bool = False, out: str = None, extra_fla
         return LIB
     nvcc = _nvcc()
     os.makedirs(obj_dir, exist_ok=True)
+    # ranks started together (torchrun) must not compile into the same object directory at once
+    import fcntl
+    lock = open(os.path.join(obj_dir, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not variant and not force and not needs_build():
+            return LIB  # another process built it while we waited
+        return _build_locked(nvcc, lib, obj_dir, variant, verbose, extra_flags)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc, lib, obj_dir, variant, verbose, extra_flags) -> str:
 
     def compile_one(job) -> str:
         src, flags, obj_name = job

@@ -198,7 +198,7 @@ class TwixTBatch {
     if (count > 0 && src_first < dst_first + count && dst_first < src_first + count)
       return fail(TWIXT_EINVAL, "clone ranges overlap");
     DeviceGuard g(device_);
-    TW_CUDA(launch_clone(rec(dst_first), rec(src_first), nullptr, count, n_, stream_));
+    TW_CUDA(launch_clone(rec(dst_first), rec(src_first), nullptr, count, n_, num_envs_, dst_first, d_stats_, stream_));
     launches_ += count > 0;
     return TWIXT_OK;
   }
@@ -218,9 +218,17 @@ class TwixTBatch {
         if (s >= dst_first && s < dst_first + count) return fail(TWIXT_EINVAL, "src_ids[%lld] lies in the destination range", (long long)i);
       }
     }
-    TW_CUDA(launch_clone(rec(dst_first), records_, static_cast<const int64_t*>(ids.dev), count, n_, stream_));
+    // device-resident ids cannot be checked here: the kernel checks every id (it skips a bad one and reports
+    // the lowest offending position), and the flag is read back before the call returns
+    TW_CUDA(cudaMemsetAsync(&d_stats_->bad_clone_index, 0xFF, sizeof(unsigned int), stream_));
+    TW_CUDA(launch_clone(rec(dst_first), records_, static_cast<const int64_t*>(ids.dev), count, n_, num_envs_,
+                         dst_first, d_stats_, stream_));
     launches_ += 1;
-    if (ids.host) TW_CUDA(cudaStreamSynchronize(stream_));
+    unsigned int bad = 0xFFFFFFFFu;
+    TW_CUDA(cudaMemcpyAsync(&bad, &d_stats_->bad_clone_index, sizeof(bad), cudaMemcpyDeviceToHost, stream_));
+    TW_CUDA(cudaStreamSynchronize(stream_));
+    if (bad != 0xFFFFFFFFu)
+      return fail(TWIXT_EINVAL, "src_ids[%u] is out of range or lies in the destination range (that env was not copied)", bad);
     return TWIXT_OK;
   }
 
@@ -229,6 +237,8 @@ class TwixTBatch {
     TW_TRY(src.CheckRange(src_first, count));
     if (src.n_ != n_) return fail(TWIXT_EINVAL, "board sizes differ: %d vs %d", src.n_, n_);
     if (count == 0) return TWIXT_OK;
+    if (&src == this && src_first < dst_first + count && dst_first < src_first + count)
+      return fail(TWIXT_EINVAL, "clone ranges overlap");
     DeviceGuard g(device_);
     const size_t bytes = static_cast<size_t>(count) * rw_ * sizeof(uint32_t);
     // order after the source batch's pending work
@@ -321,18 +331,48 @@ class TwixTBatch {
     return TWIXT_OK;
   }
 
-  int Observation(int64_t first, int64_t count, float* out) {
+  // out_mask != nullptr: the fused producer (tensor + legal mask in one pass over the records)
+  int Observation(int64_t first, int64_t count, float* out, uint8_t* out_mask) {
     TW_TRY(CheckRange(first, count));
     if (count == 0) return TWIXT_OK;
     if (out == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
     DeviceGuard g(device_);
     ScratchReset();
-    Staged o;
+    Staged o, m;
     TW_TRY(StageOut(out, static_cast<size_t>(count) * 12 * n_ * (n_ - 2) * sizeof(float), &o, false));
-    TW_CUDA(launch_observation(rec(first), count, n_, static_cast<float*>(o.dev), stream_));
+    TW_TRY(StageOut(out_mask, static_cast<size_t>(count) * n_ * n_, &m, false));
+    TW_CUDA(launch_observation(rec(first), count, n_, static_cast<float*>(o.dev), static_cast<uint8_t*>(m.dev),
+                               stream_));
     launches_ += 1;
     TW_TRY(Finish(&o));
-    return SyncIfHost(o, o);
+    TW_TRY(Finish(&m));
+    return SyncIfHost(o, m);
+  }
+
+  int Replay(int64_t first, int64_t count, const int32_t* actions, int64_t stride, const int32_t* lengths,
+             int32_t* out_applied) {
+    TW_TRY(CheckRange(first, count));
+    if (stride < 0) return fail(TWIXT_EINVAL, "stride must be >= 0");
+    if (count == 0 || stride == 0) return TWIXT_OK;
+    if (actions == nullptr) return fail(TWIXT_EINVAL, "null actions pointer");
+    DeviceGuard g(device_);
+    ScratchReset();
+    Staged in, len, ap;
+    TW_TRY(StageIn(actions, static_cast<size_t>(count) * stride * sizeof(int32_t), &in));
+    TW_TRY(StageIn(lengths, static_cast<size_t>(count) * sizeof(int32_t), &len));
+    TW_TRY(StageOut(out_applied, static_cast<size_t>(count) * sizeof(int32_t), &ap, false));
+    TW_CUDA(cudaMemsetAsync(&d_stats_->replay_illegal, 0xFF, sizeof(unsigned long long), stream_));
+    TW_CUDA(launch_replay(rec(first), count, n_, static_cast<const int32_t*>(in.dev), stride,
+                          static_cast<const int32_t*>(len.dev), static_cast<int32_t*>(ap.dev), d_stats_, stream_));
+    launches_ += 1;
+    TW_TRY(Finish(&ap));
+    if (out_applied != nullptr && !ap.host && !in.host && !len.host) return TWIXT_OK;  // asynchronous: caller inspects out_applied
+    unsigned long long bad = ~0ull;
+    TW_CUDA(cudaMemcpyAsync(&bad, &d_stats_->replay_illegal, sizeof(bad), cudaMemcpyDeviceToHost, stream_));
+    TW_CUDA(cudaStreamSynchronize(stream_));
+    if (bad != ~0ull)  // twixt.h:96, same text
+      return fail(TWIXT_EILLEGAL, "Not a legal action: %d", static_cast<int>(static_cast<int32_t>(bad & 0xFFFFFFFFull)));
+    return TWIXT_OK;
   }
 
   int Playout(int64_t first, int64_t count, int32_t max_plies, const uint64_t* stream_ids, float* out_returns,
@@ -386,17 +426,38 @@ class TwixTBatch {
     return TWIXT_OK;
   }
 
+  // Records from the caller are validated BEFORE they replace any env (validate_kernel,
+  // twixt_kernels_api.cu): a host array is staged in device scratch and checked there, a device array is
+  // checked where it lies; only then are the records copied in.  On failure the batch is untouched.
   int Import(int64_t first, int64_t count, const uint32_t* in) {
     TW_TRY(CheckRange(first, count));
     if (count == 0) return TWIXT_OK;
     if (in == nullptr) return fail(TWIXT_EINVAL, "null input pointer");
     DeviceGuard g(device_);
-    const bool dev = is_device_pointer(in);
-    TW_CUDA(cudaMemcpyAsync(rec(first), in, static_cast<size_t>(count) * rw_ * sizeof(uint32_t), cudaMemcpyDefault,
-                            stream_));
-    if (!dev) TW_CUDA(cudaStreamSynchronize(stream_));
+    const size_t bytes = static_cast<size_t>(count) * rw_ * sizeof(uint32_t);
+    if (!validate_) {  // twixt_set_validation(b, 0): trusted records (e.g. our own exports)
+      const bool dev = is_device_pointer(in);
+      TW_CUDA(cudaMemcpyAsync(rec(first), in, bytes, cudaMemcpyDefault, stream_));
+      if (!dev) TW_CUDA(cudaStreamSynchronize(stream_));
+      return TWIXT_OK;
+    }
+    ScratchReset();
+    Staged src;
+    TW_TRY(StageIn(in, bytes, &src));
+    TW_CUDA(cudaMemsetAsync(&d_stats_->invalid_code, 0xFF, sizeof(unsigned long long), stream_));
+    TW_CUDA(launch_validate(static_cast<const uint32_t*>(src.dev), count, n_, d_stats_, stream_));
+    launches_ += 1;
+    unsigned long long code = ~0ull;
+    TW_CUDA(cudaMemcpyAsync(&code, &d_stats_->invalid_code, sizeof(code), cudaMemcpyDeviceToHost, stream_));
+    TW_CUDA(cudaStreamSynchronize(stream_));
+    if (code != ~0ull)
+      return fail(TWIXT_EINVAL, "invalid state record at index %lld: %s", static_cast<long long>(code >> 8),
+                  invalid_reason_text(static_cast<unsigned>(code & 0xFFull)));
+    TW_CUDA(cudaMemcpyAsync(rec(first), src.dev, bytes, cudaMemcpyDeviceToDevice, stream_));
+    if (src.host) TW_CUDA(cudaStreamSynchronize(stream_));
     return TWIXT_OK;
   }
+  void SetValidation(bool on) { validate_ = on; }
 
   int GetStats(twixt_stats* out) {
     if (out == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
@@ -412,6 +473,7 @@ class TwixTBatch {
     out->swaps = static_cast<int64_t>(h.swaps);
     out->max_length = static_cast<int64_t>(h.max_length);
     out->kernel_launches = launches_;
+    out->debug_violations = static_cast<int64_t>(h.bounds_violations);
     return TWIXT_OK;
   }
 
@@ -486,6 +548,7 @@ class TwixTBatch {
   int64_t num_envs_ = 0;
   uint64_t seed_ = 0;
   uint64_t stream_base_ = 0;
+  bool validate_ = true;
   uint32_t* records_ = nullptr;
   DeviceStats* d_stats_ = nullptr;
   cudaStream_t stream_ = nullptr;
@@ -601,7 +664,22 @@ int twixt_returns(twixt_batch* b, int64_t first, int64_t count, float* out) {
 }
 int twixt_observation(twixt_batch* b, int64_t first, int64_t count, float* out) {
   TW_NEED(b);
-  return b->impl.Observation(first, count, out);
+  return b->impl.Observation(first, count, out, nullptr);
+}
+int twixt_observation_and_mask(twixt_batch* b, int64_t first, int64_t count, float* out_obs, uint8_t* out_mask) {
+  TW_NEED(b);
+  if (out_mask == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
+  return b->impl.Observation(first, count, out_obs, out_mask);
+}
+int twixt_replay(twixt_batch* b, int64_t first, int64_t count, const int32_t* actions, int64_t stride,
+                 const int32_t* lengths, int32_t* out_applied) {
+  TW_NEED(b);
+  return b->impl.Replay(first, count, actions, stride, lengths, out_applied);
+}
+int twixt_set_validation(twixt_batch* b, int enabled) {
+  TW_NEED(b);
+  b->impl.SetValidation(enabled != 0);
+  return TWIXT_OK;
 }
 int twixt_playout(twixt_batch* b, int64_t first, int64_t count, int32_t max_plies, const uint64_t* stream_ids,
                   float* out_returns, int32_t* out_lengths, uint16_t* out_actions, int32_t trace_plies) {
@@ -616,6 +694,30 @@ int twixt_import_state(twixt_batch* b, int64_t first, int64_t count, const uint3
   TW_NEED(b);
   return b->impl.Import(first, count, records);
 }
+// ---- multi-GPU helpers for a host that is not Python (twixt_for_open_spiel_b200/sharding.py restated) ----
+int twixt_shard_range(int64_t global_envs, int32_t world, int32_t rank, int64_t* out_first, int64_t* out_count) {
+  if (world < 1 || rank < 0 || rank >= world || global_envs < 0)
+    return fail(TWIXT_EINVAL, "bad shard arguments: %lld envs, world %d, rank %d", static_cast<long long>(global_envs),
+                world, rank);
+  if (out_first == nullptr || out_count == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
+  const int64_t base = global_envs / world, extra = global_envs % world;
+  *out_first = rank * base + (rank < extra ? rank : extra);
+  *out_count = base + (rank < extra ? 1 : 0);
+  return TWIXT_OK;
+}
+int twixt_stats_accumulate(twixt_stats* acc, const twixt_stats* part) {
+  if (acc == nullptr || part == nullptr) return fail(TWIXT_EINVAL, "null pointer");
+  acc->plies += part->plies;
+  acc->games += part->games;
+  acc->red_wins += part->red_wins;
+  acc->blue_wins += part->blue_wins;
+  acc->draws += part->draws;
+  acc->swaps += part->swaps;
+  acc->kernel_launches += part->kernel_launches;
+  if (part->max_length > acc->max_length) acc->max_length = part->max_length;
+  return TWIXT_OK;
+}
+
 int twixt_get_stats(twixt_batch* b, twixt_stats* out) {
   TW_NEED(b);
   return b->impl.GetStats(out);

@@ -72,11 +72,42 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 __host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
 
+// -DTW_PLAYOUT_BOUNDS_CHECK=1 builds the INSTRUMENTED variant used by tests/ (never the product build): every
+// shared-memory access of the rules and of the flood stack is tested against the lane's own column,
+// [0, playout_words) words, and every blocked-plane reduction against [0, n); a violation is counted in
+// DeviceStats::bounds_violations (twixt_stats.debug_violations) and the access is redirected to word 0 /
+// column 0, so a broken invariant shows up as a number instead of a fault.  The unguarded link-window and
+// flag loads are ALLOWED to leave the board (they land in this env's neighbouring planes or stack words,
+// see ld_link / ld_any below) but never the lane's column: that is what this variant proves.
+#ifndef TW_PLAYOUT_BOUNDS_CHECK
+#define TW_PLAYOUT_BOUNDS_CHECK 0
+#endif
+
 // The env's planes in shared memory (stride 32 words) + its blocked plane in HBM.
 template <int NT>
 struct PlayoutRef {
   uint32_t* p;     // smem, this lane's column
   uint32_t* gblk;  // global: the record's P_BLOCKED words
+#if TW_PLAYOUT_BOUNDS_CHECK
+  unsigned long long* viol;
+  __device__ __forceinline__ int chk(int word) const {
+    if (word < 0 || word >= playout_words(n())) {
+      atomicAdd(viol, 1ull);
+      return 0;
+    }
+    return word;
+  }
+  __device__ __forceinline__ int chk_col(int col) const {
+    if (col < 0 || col >= n()) {
+      atomicAdd(viol, 1ull);
+      return 0;
+    }
+    return col;
+  }
+#else
+  __device__ __forceinline__ int chk(int word) const { return word; }
+  __device__ __forceinline__ int chk_col(int col) const { return col; }
+#endif
   // NT is the board size (every size 5..24 is instantiated, see the end of the file).  The run-time-size
   // form (NT == 0, n_rt, count cache in shared memory) is no longer instantiated; it is kept because taking
   // it out changed ptxas' schedule of the n = 24 kernel for the worse (18.4 -> 18.8 ms, measured twice).
@@ -87,8 +118,8 @@ struct PlayoutRef {
   // n-1 (blue's end line), and a link plane holds links at their WEST endpoint, so its column n-1 is
   // empty -- which is what ld_link needs: the rules' link-window loads carry no bounds test at all.  Words
   // read further off the board belong to this env's neighbouring planes or its stack words.
-  __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[(plane * n() + col) * 32]; }
-  __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[(plane * n() + col) * 32] = v; }
+  __device__ __forceinline__ uint32_t ld(int plane, int col) const { return p[chk(plane * n() + col) * 32]; }
+  __device__ __forceinline__ void st(int plane, int col, uint32_t v) { p[chk(plane * n() + col) * 32] = v; }
   __device__ __forceinline__ uint32_t ld_link(int plane, int col) const { return ld(plane, col); }
   __device__ __forceinline__ uint32_t ld_any(int plane, int col) const { return ld(plane, col); }
   // record word (after the header) -> shared-memory word
@@ -97,7 +128,8 @@ struct PlayoutRef {
   // BSSY/BRA/BSYNC region (ten of them per move showed up as branch_resolving stalls), and redirecting
   // the store of the "false" lanes to a spare word measured slower than that
   __device__ __forceinline__ void st_if(bool c, int plane, int col, uint32_t v) {
-    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p + (plane * n() + col) * 32));
+    const int word = c ? chk(plane * n() + col) : plane * n() + col;  // only a store that happens is an access
+    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p + word * 32));
     asm volatile(
         "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp st.shared.u32 [%1], %2;\n\t}"
         :: "r"(static_cast<uint32_t>(c)), "r"(addr), "r"(v) : "memory");
@@ -109,15 +141,15 @@ struct PlayoutRef {
   __device__ __forceinline__ void st_pegs(int plane, int col, uint32_t v) { st(plane ^ 1, col, v); }
   __device__ __forceinline__ uint32_t ld_pegs_guard(int plane, int col) const { return ld_guard(plane ^ 1, col); }
   // fire-and-forget reduction (RED.OR): no load to wait for; only this thread touches the word
-  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + col, bits); }
+  __device__ __forceinline__ void or_blocked(int col, uint32_t bits) { atomicOr(gblk + chk_col(col), bits); }
   // Three UNCONDITIONAL reductions per move: OR-ing zero bits is harmless (and a column left of the board
   // only ever gets zero bits: its address is clamped).  ptxas cannot predicate a RED -- every conditional
   // one becomes its own branch region (three of them cost 9 %), and even one branch around all three
   // (taken by half of the moves) was 2.5 % slower than always issuing them.
   __device__ __forceinline__ void or_blocked3(int x, const uint32_t blk[3]) {
-    atomicOr(gblk + x, blk[0]);
-    atomicOr(gblk + max(x - 1, 0), blk[1]);
-    atomicOr(gblk + max(x - 2, 0), blk[2]);
+    atomicOr(gblk + chk_col(x), blk[0]);
+    atomicOr(gblk + chk_col(max(x - 1, 0)), blk[1]);
+    atomicOr(gblk + chk_col(max(x - 2, 0)), blk[2]);
   }
   // per-column count cache (twixt_engine.cuh, count_cache_*).  With a compile-time board size every index
   // into it is static after unrolling, so the six words live in REGISTERS (no load before a selection, no
@@ -155,6 +187,18 @@ struct SmemStack {
   uint32_t base_addr;  // ... as a shared-space address
   uint32_t top_addr;   // address one entry past the top; entries are 32 words = 128 bytes apart
   bool overflow;
+#if TW_PLAYOUT_BOUNDS_CHECK
+  unsigned long long* viol;
+  __device__ __forceinline__ uint32_t chk(uint32_t addr) const {
+    if (addr < base_addr || addr >= base_addr + kStackWords * 128u) {
+      atomicAdd(viol, 1ull);
+      return base_addr;
+    }
+    return addr;
+  }
+#else
+  __device__ __forceinline__ uint32_t chk(uint32_t addr) const { return addr; }
+#endif
   __device__ __forceinline__ void init(uint32_t* first_word) {
     base = first_word;
     base_addr = static_cast<uint32_t>(__cvta_generic_to_shared(first_word));
@@ -174,7 +218,7 @@ struct SmemStack {
       const bool doit = c[i] && room;
       asm volatile(
           "{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %0, 0;\n\t@pp st.shared.u32 [%1], %2;\n\t}"
-          :: "r"(static_cast<uint32_t>(doit)), "r"(top_addr), "r"(e[i]) : "memory");
+          :: "r"(static_cast<uint32_t>(doit)), "r"(doit ? chk(top_addr) : top_addr), "r"(e[i]) : "memory");
       top_addr += doit ? 128u : 0u;
     }
   }
@@ -183,7 +227,7 @@ struct SmemStack {
     const bool have = top_addr != base_addr;
     top_addr -= have ? 128u : 0u;
     uint32_t t;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(top_addr) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(chk(top_addr)) : "memory");
     return have ? t : otherwise;
   }
 };
@@ -221,6 +265,10 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
   for (int i = 0; i < kCacheWords; ++i) b.cw[i] = 0u;
   SmemStack stk;
   stk.init(mine + kSmemPlanes * n * 32);
+#if TW_PLAYOUT_BOUNDS_CHECK
+  b.viol = &a.stats->bounds_violations;
+  stk.viol = &a.stats->bounds_violations;
+#endif
   uint32_t s_lo = 0, s_hi = 0;
   // Random words: block `rq` (moves 4rq..4rq+3) in ra[], block rq+1 in rb[].  Lanes of a warp are at
   // different move numbers, so blocks are produced on a warp-uniform schedule (every 4th iteration, all

@@ -22,6 +22,15 @@ struct DeviceStats {
   unsigned int pad;
   // ticket counter of the persistent playout kernel (zeroed before every launch)
   unsigned long long tickets;
+  // validate kernel: (lowest invalid env << 8) | reason, all ones = every record passed
+  unsigned long long invalid_code;
+  // replay kernel: (lowest env that met an illegal action << 32) | that action, all ones = none
+  unsigned long long replay_illegal;
+  // clone kernel: lowest position whose gathered source id was out of range / inside the destination
+  unsigned int bad_clone_index;
+  unsigned int pad2;
+  // only written by the bounds-instrumented test variant of the playout kernel (TW_PLAYOUT_BOUNDS_CHECK)
+  unsigned long long bounds_violations;
 };
 
 struct PlayoutArgs {
@@ -42,7 +51,11 @@ struct PlayoutArgs {
 
 cudaError_t launch_reset(uint32_t* records, int64_t count, int n, cudaStream_t s);
 cudaError_t launch_clone(uint32_t* dst, const uint32_t* src, const int64_t* src_ids, int64_t count, int n,
-                         cudaStream_t s);
+                         int64_t num_envs, int64_t dst_first, DeviceStats* stats, cudaStream_t s);
+cudaError_t launch_replay(uint32_t* records, int64_t count, int n, const int32_t* actions, int64_t stride,
+                          const int32_t* lengths, int32_t* out_applied, DeviceStats* stats, cudaStream_t s);
+cudaError_t launch_validate(const uint32_t* records, int64_t count, int n, DeviceStats* stats, cudaStream_t s);
+const char* invalid_reason_text(unsigned code);
 cudaError_t launch_legal_actions(const uint32_t* records, int64_t count, int n, void* out_actions, int elem_bytes,
                                  int64_t stride, int32_t* out_counts, cudaStream_t s);
 cudaError_t launch_legal_mask(const uint32_t* records, int64_t count, int n, uint8_t* out, cudaStream_t s);
@@ -50,7 +63,8 @@ cudaError_t launch_apply(uint32_t* records, int64_t count, int n, const int32_t*
                          DeviceStats* stats, cudaStream_t s);
 cudaError_t launch_query(const uint32_t* records, int64_t count, int n, int8_t* out_player, uint8_t* out_terminal,
                          float* out_returns, cudaStream_t s);
-cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, float* out, cudaStream_t s);
+cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, float* out, uint8_t* out_mask,
+                               cudaStream_t s);
 cudaError_t launch_playout(const PlayoutArgs& a, cudaStream_t s);
 // one-time per-process setup of the playout kernels (opt-in shared memory)
 cudaError_t playout_setup();

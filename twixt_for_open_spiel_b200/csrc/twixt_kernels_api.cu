@@ -5,12 +5,15 @@
 // All of them are HBM-bound byte/bit work (no tensor cores: nothing here is a
 // contraction).  Mapping:
 //   reset / clone       one thread per 16-byte piece of a record (128-bit stores)
-//   legal list / mask   one warp per env, lane = board column; popc + warp
-//                       prefix sum compacts the ascending action list
-//   apply               one thread per env working in place on its record
+//   legal list / mask   persistent warps (grid = SMs x occupancy), one env per
+//                       warp at a time, lane = board column; popc + ballot
+//                       prefix sum places each lane's chunk of the ascending
+//                       action list; inputs fetched one env ahead
+//   apply / replay      one thread per env working in place on its record
 //                       (touches only the few words a move needs)
-//   observation         one block per env, planes staged in shared memory,
-//                       float4 stores
+//   observation(+mask)  persistent blocks, one env per block at a time, record
+//                       staged in shared memory one env ahead, float4 stores
+//   validate            one warp per imported record, lane = board column
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,15 +57,26 @@ __global__ void reset_kernel(uint32_t* __restrict__ records, int64_t count, int 
 }
 
 // ---------------------------------------------------------------- clone ---
-// State::Clone (twixt.h:80-82): dst env i <- src env (src_ids ? src_ids[i] : i)
+// State::Clone (twixt.h:80-82): dst env i <- src env (src_ids ? src_ids[i] : i).
+// Gathered ids are checked HERE (they may live on the device, where the host cannot see them): an id outside
+// [0, num_envs) or inside the destination range [dst_first, dst_first + count) copies nothing and is
+// reported through stats->bad_clone_index (lowest offending position), like apply reports illegal actions.
 __global__ void clone_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
-                             const int64_t* __restrict__ src_ids, int64_t count, int quads_per_record) {
+                             const int64_t* __restrict__ src_ids, int64_t count, int quads_per_record,
+                             int64_t num_envs, int64_t dst_first, DeviceStats* __restrict__ stats) {
   const int64_t total = count * quads_per_record;
   for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < total;
        q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t env = q / quads_per_record;
     const int in_rec = static_cast<int>(q - env * quads_per_record);
-    const int64_t from = src_ids ? src_ids[env] : env;
+    int64_t from = env;
+    if (src_ids != nullptr) {
+      from = src_ids[env];
+      if (from < 0 || from >= num_envs || (from >= dst_first && from < dst_first + count)) {
+        if (in_rec == 0) atomicMin(&stats->bad_clone_index, static_cast<unsigned int>(env));
+        continue;
+      }
+    }
     reinterpret_cast<uint4*>(dst)[q] = __ldg(reinterpret_cast<const uint4*>(src) + from * quads_per_record + in_rec);
   }
 }
@@ -283,6 +297,133 @@ __global__ void apply_kernel(uint32_t* __restrict__ records, int64_t count, int 
   if (out_status != nullptr) out_status[i] = status;
 }
 
+// --------------------------------------------------------------- replay ---
+// A whole action history per env in ONE launch (upstream serialises a state as its action history and
+// deserialises by replaying it, spiel.cc State::Serialize / Game::DeserializeState; here that replay runs on
+// the device instead of one apply launch per move).  actions is [count, stride] int32, env i applies
+// actions[i*stride + 0 .. len_i) in order from its CURRENT state with the legality test of DoApplyAction
+// (twixt.h:93-104); len_i = lengths[i] if given, else the row up to its first negative entry.  An env stops
+// at its first illegal action (state as reached so far); out_applied[i] = moves made.
+__global__ void replay_kernel(uint32_t* __restrict__ records, int64_t count, int n, int rw,
+                              const int32_t* __restrict__ actions, int64_t stride, const int32_t* __restrict__ lengths,
+                              int32_t* __restrict__ out_applied, DeviceStats* __restrict__ stats) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  RecordRef<1> b{records + i * rw, n};
+  const uint4 hw = *reinterpret_cast<const uint4*>(b.p);
+  Header h;
+  unpack_header(hw.x, hw.y, hw.z, hw.w, h);
+  const int32_t* row = actions + i * stride;
+  const int64_t len = lengths != nullptr ? static_cast<int64_t>(lengths[i]) : stride;
+  int k = 0;
+  for (; k < len && k < stride; ++k) {
+    const int action = row[k];
+    if (action < 0) break;
+    if (!is_legal(b, h, action)) {
+      // lowest env first; the low word carries the action for the host's message (twixt.h:96)
+      atomicMin(&stats->replay_illegal, (static_cast<unsigned long long>(i) << 32) | static_cast<uint32_t>(action));
+      break;
+    }
+    const int x = action / n;
+    apply_legal_cell<kFloodStack>(b, h, x, action - x * n);
+  }
+  uint4 o;
+  pack_header(h, o.x, o.y, o.z, o.w);
+  *reinterpret_cast<uint4*>(b.p) = o;
+  if (out_applied != nullptr) out_applied[i] = k;
+}
+
+// ------------------------------------------------------------- validate ---
+// twixt_import_state takes records from the caller, and the fused playout kernel reads records with its
+// bounds tests deliberately removed (twixt_kernel_playout.cu, PlayoutRef), so what comes in is checked first.
+// The reference can only reach a state through DoApplyAction (twixt.h:93-104); these are the invariants
+// every reachable record has and every kernel relies on.  One warp per record, lane = board column:
+//   header     result/swapped bits only, ply <= n*n-3, swapped => ply >= 2, result != open => ply >= 1
+//   rows       no plane has a bit at a row >= n; padding words are zero
+//   pegs       red and blue disjoint; red never in column 0 / n-1, blue never in row 0 / n-1
+//              (twixtboard.cc:252-276; the corners follow), popc(red) = ceil(ply/2) - swapped, popc(blue) = ply/2
+//   first move word 2 = 0xFFFFFFFF iff ply = 0, else a red first move whose peg (or, after a swap, the blue
+//              peg on the turned cell, twixtboard.cc:465-475) is on the board
+//   links      a link bit sits on a peg whose knight neighbour in that direction holds a peg of the same
+//              colour (so link planes are empty in the columns a link cannot start from)
+//   flags      border / blocked bits only on pegs
+//   counts     word 3 = empty cells red / blue may still play on, recounted
+// The lowest failing env and its reason go to stats->invalid_code by one 64-bit atomicMin.
+enum : uint32_t {
+  kBadHeader = 1, kBadRows = 2, kBadPegs = 3, kBadFirstMove = 4, kBadLinks = 5, kBadFlags = 6, kBadCounts = 7,
+  kBadPadding = 8
+};
+
+__global__ void __launch_bounds__(256) validate_kernel(const uint32_t* __restrict__ records, int64_t count, int n,
+                                                       int rw, DeviceStats* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t env = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); env < count;
+       env += nwarps) {
+    const uint32_t* rec = records + env * rw;
+    const uint4 hw = ldg128(rec);
+    const bool on = lane < n;
+    uint32_t w[kNumStatePlanes];
+#pragma unroll
+    for (int p = 0; p < kNumStatePlanes; ++p) w[p] = on ? __ldg(rec + kHeaderWords + p * n + lane) : 0u;
+    const int pad = rw - (kHeaderWords + kNumStatePlanes * n);
+    const uint32_t padw = lane < pad ? __ldg(rec + kHeaderWords + kNumStatePlanes * n + lane) : 0u;
+    uint32_t bad = 0xFFu;
+    const auto flag = [&](bool c, uint32_t code) { bad = (c && code < bad) ? code : bad; };
+    const uint32_t full = full_rows(n), inner = inner_rows(n);
+    const uint32_t red = w[P_RED], blue = w[P_BLUE], occ = red | blue;
+    uint32_t off_rows = 0;
+#pragma unroll
+    for (int p = 0; p < kNumStatePlanes; ++p) off_rows |= w[p] & ~full;
+    flag(off_rows != 0u, kBadRows);
+    flag(padw != 0u, kBadPadding);
+    flag((red & blue) != 0u, kBadPegs);
+    flag((lane == 0 || lane == n - 1) && red != 0u, kBadPegs);
+    flag((blue & ~inner) != 0u, kBadPegs);
+    flag(((w[P_START] | w[P_END] | w[P_BLOCKED]) & ~occ) != 0u, kBadFlags);
+    // pegs one and two columns to the east (lanes >= n hold zeros; n <= 24 keeps lane + 2 inside the warp)
+    const uint32_t r1 = __shfl_down_sync(kFullMask, red, 1), r2 = __shfl_down_sync(kFullMask, red, 2);
+    const uint32_t b1 = __shfl_down_sync(kFullMask, blue, 1), b2 = __shfl_down_sync(kFullMask, blue, 2);
+    const uint32_t ok_nne = (red & (r1 >> 2)) | (blue & (b1 >> 2));  // (x+1, y+2)
+    const uint32_t ok_ene = (red & (r2 >> 1)) | (blue & (b2 >> 1));  // (x+2, y+1)
+    const uint32_t ok_ese = (red & (r2 << 1)) | (blue & (b2 << 1));  // (x+2, y-1)
+    const uint32_t ok_sse = (red & (r1 << 2)) | (blue & (b1 << 2));  // (x+1, y-2)
+    flag(((w[P_LINK0] & ~ok_nne) | (w[P_LINK0 + 1] & ~ok_ene) | (w[P_LINK0 + 2] & ~ok_ese) |
+          (w[P_LINK0 + 3] & ~ok_sse)) != 0u, kBadLinks);
+    // recount: empty playable cells (both fit 16 bits: at most n*(n-2) = 528) and pegs per colour
+    uint32_t open2 = ((lane >= 1 && lane <= n - 2) ? __popc(full & ~occ) : 0) | ((on ? __popc(inner & ~occ) : 0) << 16);
+    uint32_t pegs2 = __popc(red) | (__popc(blue) << 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      open2 += __shfl_xor_sync(kFullMask, open2, o);
+      pegs2 += __shfl_xor_sync(kFullMask, pegs2, o);
+    }
+    const uint32_t ply = hw.x, res = hw.y & 3u, swapped = (hw.y >> 2) & 1u;
+    flag((hw.y >> 3) != 0u || ply > static_cast<uint32_t>(n * n - 3) || (swapped && ply < 2u) ||
+             (res != kOpen && ply == 0u), kBadHeader);
+    flag(hw.w != open2, kBadCounts);
+    flag(pegs2 != (((ply + 1u) / 2u - swapped) | ((ply / 2u) << 16)), kBadCounts);
+    if (ply == 0u) {
+      flag(hw.z != kNoMove, kBadFirstMove);
+    } else {
+      const uint32_t mo = hw.z;
+      const int mx = static_cast<int>(mo) / n, my = static_cast<int>(mo) - mx * n;
+      const bool in_range = mo < static_cast<uint32_t>(n * n) && mx >= 1 && mx <= n - 2;
+      flag(!in_range, kBadFirstMove);
+      if (in_range) {
+        // the first peg: red on the cell itself, or blue on the cell turned by 90 degrees after a swap
+        const int px = swapped ? my : mx, py = swapped ? n - 1 - mx : my;
+        const uint32_t pegs = swapped ? blue : red;
+        const bool there = __any_sync(kFullMask, lane == px && ((pegs >> py) & 1u));
+        flag(!there, kBadFirstMove);
+      }
+    }
+    bad = __reduce_min_sync(kFullMask, bad);
+    if (lane == 0 && bad != 0xFFu)
+      atomicMin(&stats->invalid_code, (static_cast<unsigned long long>(env) << 8) | bad);
+  }
+}
+
 // ---------------------------------------------------------------- query ---
 // CurrentPlayer twixt.h:38, IsTerminal twixt.h:45-48, Returns twixt.h:50-63.
 __global__ void query_kernel(const uint32_t* __restrict__ records, int64_t count, int rw,
@@ -319,9 +460,15 @@ constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
 constexpr int kObsStreamWords = (12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2) + 31) / 32;
 constexpr int kObsRecordWords = kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE;  // 220 <= 256 threads
 
-template <bool kVec4>
+//
+// kMask: the same pass also writes the env's [n*n] uint8 legal-action mask (upstream LegalActionsMask; the
+// AlphaZero-style producer of BASELINE config C5 wants both), so the record is read from HBM once for the
+// two outputs.  The mask is 576 of the 25 920 output bytes at n = 24.
+template <bool kVec4, bool kMask>
 __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t* __restrict__ records, int64_t count,
-                                                                  int n, int rw, float* __restrict__ out) {
+                                                                  int n, int rw, float* __restrict__ out,
+                                                                  uint8_t* __restrict__ out_mask) {
+  __shared__ uint32_t legalw[TWIXT_MAX_BOARD_SIZE];               // kMask: legal cells per column
   __shared__ __align__(16) uint32_t rec[kObsRecordWords + 4];  // the env's record
   __shared__ uint32_t planes[kObsPlaneWords];                  // [12][n] column words, board coordinates
   __shared__ uint32_t rowbits[kObsPlaneWords];                 // [12][n] output rows, bit c = tensor column c
@@ -347,7 +494,33 @@ __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t
       const int p = t / n;
       planes[t] = obs_plane_word(b, p, t - p * n);
     }
+    if (kMask && tid < n) {  // TwixTState::LegalActions (twixt.h:86-90) as a bit word per column
+      Header h;
+      unpack_header(rec[0], rec[1], rec[2], rec[3], h);
+      legalw[tid] = h.result != kOpen ? 0u : legal_word(b, h, tid);
+    }
     __syncthreads();
+    if (kMask) {
+      const int cells = n * n;
+      uint8_t* mdst = out_mask + env * static_cast<int64_t>(cells);
+      if ((cells & 3) == 0 && (reinterpret_cast<uintptr_t>(out_mask) & 3u) == 0) {
+        for (int q = tid; q < (cells >> 2); q += kObsThreads) {  // four consecutive cells -> one 4-byte store
+          int x = (4 * q) / n, y = 4 * q - x * n;
+          uint32_t v = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v |= ((legalw[x] >> y) & 1u) << (8 * j);
+            if (++y == n) { y = 0; ++x; }
+          }
+          reinterpret_cast<uint32_t*>(mdst)[q] = v;
+        }
+      } else {
+        for (int c = tid; c < cells; c += kObsThreads) {
+          const int x = c / n;
+          mdst[c] = static_cast<uint8_t>((legalw[x] >> (c - x * n)) & 1u);
+        }
+      }
+    }
     for (int t = tid; t < rows; t += kObsThreads) {
       const int p = t / n, r = t - p * n;
       uint32_t bits = 0;
@@ -425,10 +598,11 @@ cudaError_t launch_reset(uint32_t* records, int64_t count, int n, cudaStream_t s
 }
 
 cudaError_t launch_clone(uint32_t* dst, const uint32_t* src, const int64_t* src_ids, int64_t count, int n,
-                         cudaStream_t s) {
+                         int64_t num_envs, int64_t dst_first, DeviceStats* stats, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   const int quads = record_words(n) / 4;
-  clone_kernel<<<grid_for(count * quads, 256), 256, 0, s>>>(dst, src, src_ids, count, quads);
+  clone_kernel<<<grid_for(count * quads, 256), 256, 0, s>>>(dst, src, src_ids, count, quads, num_envs, dst_first,
+                                                           stats);
   return cudaGetLastError();
 }
 
@@ -483,6 +657,36 @@ cudaError_t launch_apply(uint32_t* records, int64_t count, int n, const int32_t*
   return cudaGetLastError();
 }
 
+cudaError_t launch_replay(uint32_t* records, int64_t count, int n, const int32_t* actions, int64_t stride,
+                          const int32_t* lengths, int32_t* out_applied, DeviceStats* stats, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  const int threads = 128;
+  const int64_t blocks = (count + threads - 1) / threads;
+  replay_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(records, count, n, record_words(n), actions, stride,
+                                                                  lengths, out_applied, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_validate(const uint32_t* records, int64_t count, int n, DeviceStats* stats, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  validate_kernel<<<grid_for(count, 8, 148 * 16), 256, 0, s>>>(records, count, n, record_words(n), stats);
+  return cudaGetLastError();
+}
+
+const char* invalid_reason_text(unsigned code) {
+  switch (code) {
+    case kBadHeader: return "header (ply / result / swapped) out of range";
+    case kBadRows: return "a plane has bits at rows >= board_size";
+    case kBadPegs: return "pegs overlap, stand on a foreign border line, or their number does not fit the ply";
+    case kBadFirstMove: return "first-move word does not match the board";
+    case kBadLinks: return "a link bit has no same-colour pegs at both ends";
+    case kBadFlags: return "border / blocked flags on an empty cell";
+    case kBadCounts: return "peg or empty-cell counts do not match the planes";
+    case kBadPadding: return "padding words are not zero";
+    default: return "unknown";
+  }
+}
+
 cudaError_t launch_query(const uint32_t* records, int64_t count, int n, int8_t* out_player, uint8_t* out_terminal,
                          float* out_returns, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
@@ -493,16 +697,20 @@ cudaError_t launch_query(const uint32_t* records, int64_t count, int n, int8_t* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, float* out, cudaStream_t s) {
+cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, float* out, uint8_t* out_mask,
+                               cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   const int rw = record_words(n);
   const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  if (vec) {
-    const auto k = observation_kernel<true>;
-    k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+  const auto go = [&](auto k) {
+    k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out, out_mask);
+  };
+  if (out_mask != nullptr) {
+    if (vec) go(observation_kernel<true, true>);
+    else go(observation_kernel<false, true>);
   } else {
-    const auto k = observation_kernel<false>;
-    k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out);
+    if (vec) go(observation_kernel<true, false>);
+    else go(observation_kernel<false, false>);
   }
   return cudaGetLastError();
 }

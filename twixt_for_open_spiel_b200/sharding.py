@@ -19,9 +19,13 @@ def shard_range(global_envs: int, world: int, rank: int) -> Tuple[int, int]:
     """(first global env id, count) of `rank`'s shard; shards differ by at most one env."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad world/rank: %d/%d" % (world, rank))
-    base, extra = divmod(int(global_envs), world)
-    first = rank * base + min(rank, extra)
-    return first, base + (1 if rank < extra else 0)
+    # the C ABI's helper (twixt_shard_range), so that a C++ host and this module cut the env range identically
+    import ctypes as C
+    from . import _lib
+    first, count = C.c_int64(), C.c_int64()
+    if _lib.load().twixt_shard_range(int(global_envs), world, rank, C.byref(first), C.byref(count)) != 0:
+        raise ValueError(_lib.load().twixt_last_error().decode())
+    return int(first.value), int(count.value)
 
 
 def reduce_counters(counters: Dict[str, int], dist=None, device=None) -> Dict[str, int]:

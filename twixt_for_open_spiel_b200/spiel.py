@@ -130,10 +130,16 @@ class TwixTGame:
 
     # -- serialisation (upstream serialises a state as its action history) --------
     def deserialize_state(self, text: str) -> "TwixTState":
-        """Inverse of TwixTState.serialize(): replays the action history on the device."""
+        """Inverse of TwixTState.serialize(): the whole action history is replayed on the device by ONE
+        launch (twixt_replay); an illegal action in it raises "Not a legal action: N" like ApplyAction."""
+        history = [int(tok) for tok in text.replace(",", " ").split()]
+        for a in history:
+            if a < 0 or a > 0x7FFFFFFF:
+                raise SpielFatalError("Not a legal action: %d" % a)
         state = self.new_initial_state()
-        for tok in text.replace(",", " ").split():
-            state.apply_action(int(tok))
+        if history:
+            state._pool.replay(np.asarray([history], dtype=np.int32), state._idx)
+            state._history = history
         return state
 
     def new_state_from_record(self, record) -> "TwixTState":
