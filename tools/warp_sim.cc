@@ -32,11 +32,46 @@ struct CachedRec : public RecordRef<1> {
   }
 };
 
+// A flood work list that MERGES entries of the same column: one frontier word per board column + a dirty mask.
+// Drop-in for the stack interface used by flood_visit_entry.
+struct FrontierStack {
+  uint32_t f[24];
+  uint32_t dirty = 0;
+  int sp = 0;  // number of dirty columns (for the depth histogram)
+  bool overflow = false;
+  FrontierStack() { for (auto& w : f) w = 0; }
+  bool empty() const { return dirty == 0; }
+  void push(uint32_t e) {
+    const int c = static_cast<int>(e >> 24);
+    f[c] |= e & 0xFFFFFFu;
+    dirty |= 1u << c;
+    sp = __builtin_popcount(dirty);
+  }
+  void push4_if(const bool c[4], const uint32_t e[4]) {
+    for (int i = 0; i < 4; ++i) if (c[i]) push(e[i]);
+  }
+  uint32_t top() const {
+    const int c = __builtin_ctz(dirty);
+    return (static_cast<uint32_t>(c) << 24) | f[c];
+  }
+  void pop() {
+    const int c = __builtin_ctz(dirty);
+    f[c] = 0;
+    dirty &= dirty - 1;
+    sp = __builtin_popcount(dirty);
+  }
+};
+#ifdef SIM_FRONTIER
+using SimStack = FrontierStack;
+#else
+using SimStack = LocalStack<64>;
+#endif
+
 struct Lane {
   std::vector<uint32_t> rec;
   CachedRec b;
   Header h;
-  LocalStack<64> stk;
+  SimStack stk;
   uint32_t pendc[2] = {0, 0}, originc[2] = {0, 0};
   int run_colour = 0, fplane = P_START;
   bool playing = false, have = false;
@@ -64,6 +99,7 @@ int main(int argc, char** argv) {
   double cost = 0;
   long iters = 0, it_move = 0, it_flood = 0, lanes_move = 0, lanes_flood = 0, plies = 0, floods = 0, visits = 0;
   long hist[16] = {0};
+  long depth_hist[66] = {0};
   for (int w = 0; w < warps; ++w) {
     std::vector<Lane> L(32);
     int next_game[32];
@@ -82,7 +118,7 @@ int main(int argc, char** argv) {
       a.playing = true;
       a.have = true;
       a.pendc[0] = a.pendc[1] = 0;
-      a.stk = LocalStack<64>();
+      a.stk = SimStack();
       select_legal(a.b, a.h, static_cast<int>(playout_index(word_for(seed, a.stream, 0), legal_count(a.h, n))), a.sx, a.sy);
       a.swap_next = false;
       a.load_wait = 1;
@@ -172,6 +208,7 @@ int main(int argc, char** argv) {
             a.stk.pop();
           }
           flood_visit_entry(a.b, a.fplane, a.stk, e);
+          depth_hist[a.stk.sp]++;
           ++cur_visits[l];
           if (a.stk.empty()) {
             hist[cur_visits[l] < 15 ? cur_visits[l] : 15]++;
@@ -189,6 +226,13 @@ int main(int argc, char** argv) {
          double(floods) / plies, double(visits) / plies, cost / plies * 1.0, cost * 32 / plies);
   printf("  visits-per-flood(plane) histogram:");
   for (int i = 1; i < 16; ++i) printf(" %d:%ld", i, hist[i]);
+  printf("\n  stack depth after a visit (entries): ");
+  long tot = 0, acc = 0;
+  for (int i = 0; i < 66; ++i) tot += depth_hist[i];
+  for (int i = 0; i < 66; ++i) {
+    acc += depth_hist[i];
+    if (depth_hist[i]) printf(" %d:%.5f", i, 1.0 - double(acc) / tot);
+  }
   printf("\n");
   return 0;
 }

@@ -16,10 +16,17 @@ import numpy as np
 
 from . import _lib
 
-try:  # torch is plumbing only (device buffers, streams); optional here
-    import torch
-except Exception:  # pragma: no cover
-    torch = None
+# torch is plumbing only (device buffers, streams) and is imported LAZILY: a host that hands over numpy
+# arrays -- e.g. the per-board-size worker processes of the reference-parity tests -- never pays for it.
+torch = None
+
+
+def _torch():
+    global torch
+    if torch is None:
+        import torch as _t
+        torch = _t
+    return torch
 
 
 class SpielFatalError(RuntimeError):
@@ -31,7 +38,9 @@ class TwixTCudaError(RuntimeError):
 
 
 def _is_torch(a) -> bool:
-    return torch is not None and isinstance(a, torch.Tensor)
+    if not type(a).__module__.startswith("torch"):
+        return False
+    return isinstance(a, _torch().Tensor)
 
 
 def _ptr(a, dtype=None, min_elems: int = 0) -> int:
@@ -41,7 +50,7 @@ def _ptr(a, dtype=None, min_elems: int = 0) -> int:
     if _is_torch(a):
         if not a.is_contiguous():
             raise ValueError("tensor must be contiguous")
-        if dtype is not None and a.dtype != dtype[1]:
+        if dtype is not None and a.dtype != getattr(_torch(), dtype[1]):
             raise TypeError("expected torch dtype %s, got %s" % (dtype[1], a.dtype))
         if a.numel() < min_elems:
             raise ValueError("tensor too small: %d < %d" % (a.numel(), min_elems))
@@ -58,7 +67,7 @@ def _ptr(a, dtype=None, min_elems: int = 0) -> int:
 
 
 def _dt(np_dtype, torch_name: str):
-    return (np.dtype(np_dtype), getattr(torch, torch_name) if torch is not None else None)
+    return (np.dtype(np_dtype), torch_name)  # the torch dtype is resolved by _ptr, only for torch tensors
 
 
 def game_info(board_size: int) -> _lib.GameInfo:
@@ -125,7 +134,7 @@ class TwixTBatch:
 
     def use_torch_stream(self):
         """Launch on torch's current stream so torch.cuda.Event timing brackets our kernels."""
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.set_stream(_torch().cuda.current_stream(self.device).cuda_stream)
 
     def synchronize(self):
         self._check(self._lib.twixt_synchronize(self._h))

@@ -241,13 +241,38 @@ struct LinkWindow {
   uint32_t w[4][5];
 };
 
+// How the link window is aligned to the new peg's row.  TW_ALIGN_MUL = 0: (word << 5) >> y, row y+oy at bit
+// oy+5 -- two shifts per word on the integer-ALU pipe, the busiest pipe of the playout kernel (74 %).
+// TW_ALIGN_MUL = 1: word * 2^(28-y), row y+oy at bit oy+28 -- ONE multiply per word, which issues on the FMA
+// pipe (13 % busy); rows above y+3 leave the word at the top, rows below y-2 stay in the low bits where no
+// crossing mask looks (the masks of twixt_crossing.inc cover oy = -2 .. +3, i.e. bits 26 .. 31 here).
+#ifndef TW_ALIGN_MUL
+#define TW_ALIGN_MUL 1
+#endif
+enum : int { kAlignShift = TW_ALIGN_MUL ? 23 : 0 };
+
+TW_HD uint32_t align_factor(int y) { return TW_ALIGN_MUL ? (1u << (28 - y)) : static_cast<uint32_t>(y); }
+TW_HD uint32_t align_word(uint32_t w, uint32_t factor) {
+#if TW_ALIGN_MUL
+#if defined(__CUDA_ARCH__)
+  uint32_t r;  // (inline PTX: the optimiser would turn a multiply by 1 << s back into a shift)
+  asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(factor));
+  return r;
+#else
+  return w * factor;
+#endif
+#else
+  return (w << 5) >> factor;
+#endif
+}
+
 // Would the link from the new peg (x, y) in Compass direction d be crossed by
 // an existing link, of either colour (twixtboard.cc:519-527 tests HasLink
-// only)?  `ly` is the window with every word aligned to the peg's row,
-// (word << 5) >> y, so that row y+oy sits at bit oy+5 and each of the 5..7
-// tests of a direction is one AND with a constant (twixt_crossing.inc).
+// only)?  `ly` is the window with every word aligned to the peg's row (see
+// above), so that each of the 5..7 tests of a direction is one AND with a
+// constant (twixt_crossing.inc, masks written for row y+oy at bit oy+5).
 TW_HD bool crossing_blocked(const LinkWindow& ly, int d) {
-#define TW_X(plane, c, mask) (ly.w[plane][c] & (mask))
+#define TW_X(plane, c, mask) (ly.w[plane][c] & (static_cast<uint32_t>(mask) << kAlignShift))
 #define TW_CROSS_CASE(dir, expr) \
   case dir:                      \
     return (expr) != 0u;
@@ -452,6 +477,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
     LinkWindow lw, ly;
     uint32_t fs[5], fe[5];  // border flags of columns x-2 .. x+2
     uint32_t blk[3] = {0u, 0u, 0u};  // new blocked-east bits of columns x, x-1, x-2
+    const uint32_t factor = align_factor(y);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -461,7 +487,7 @@ TW_HD bool link_move(B& b, const Placement& p, uint32_t& pending) {
 #endif
       for (int pl = 0; pl < 4; ++pl) {
         lw.w[pl][c] = b.ld_link(P_LINK0 + pl, x - 3 + c);
-        ly.w[pl][c] = (lw.w[pl][c] << 5) >> y;  // row y+oy at bit oy+5
+        ly.w[pl][c] = align_word(lw.w[pl][c], factor);  // the new peg's row at a fixed bit
       }
       fs[c] = b.ld_any(P_START, x - 2 + c);  // only read under made[c], which is empty off the board
       fe[c] = b.ld_any(P_END, x - 2 + c);
