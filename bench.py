@@ -16,9 +16,17 @@ Prints ONE JSON line (see the key list in the task contract):
   e2e        the same metric through the C ABI with HOST (pinned) buffers:
              per step the per-env stream ids go host->device and returns +
              lengths come device->host inside the timed region
-  roofline   the fused playout kernel against the measured HBM peak, using the
-             algorithmic-bytes convention of SURVEY.md section 8(d): 2*S(24) =
-             1328 B per env-step
+  roofline   the fused playout kernel against its PHYSICAL ceiling, the issue slots
+             of the device (148 SMs x 4 schedulers x f_SM x 32 lanes / thread-
+             instructions per ply, the latter from the committed ncu capture of
+             this build, profiles/r2_playout_ncu.json); the algorithmic-bytes
+             convention of SURVEY.md section 8(d) (2*S(24) = 1328 B per env-step
+             against the measured HBM peak) is kept beside it as `hbm_convention`
+  configs    the other BASELINE.json configs that are benchmarks: c1_n8 (1 Mi-env
+             playouts at n=8) and c3_n12 (4 096 MCTS leaves x 4 rollouts), each
+             with the reference's CPU path timed beside it
+  adapter_latency_us   per-call cost of the single-state calls a drop-in adapter
+             makes (count = 1, host buffers), beside the reference's own ns
   cpu_baseline  the reference's own CPU path (oracle/_ref/ref_bench: unmodified
              reference sources) on this host's cores, bounded sample
 `--impl reference` times only that CPU path, as the reference arm.
@@ -50,9 +58,11 @@ def _peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def _traffic():
-    """Per-launch DRAM bytes of the playout kernel from the committed ncu capture, if any."""
-    path = os.path.join(ROOT, "profiles", "playout_dram_traffic.json")
+def _playout_capture():
+    """Counters of the playout kernel from the committed `ncu --set full` capture of THIS build
+    (tools/ncu_playout_json.py writes it from the .ncu-rep): warp instructions, active lanes, issue-active,
+    ALU pipe, DRAM bytes -- all per launch of the bench's own workload."""
+    path = os.path.join(ROOT, "profiles", "r2_playout_ncu.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f)
@@ -146,6 +156,12 @@ def _port_worker(board_size, seconds, seed):
     return int(plies), int(games.value), float(el.value)
 
 
+def cpu_reference_raw(board_size: int, workers: int, seconds: float, mode: str):
+    """oracle/_ref/ref_bench in one of its other modes ("rollout", "latency"); None if it is not built."""
+    from oracle import pyoracle
+    return pyoracle.run_ref_bench(board_size, workers, seconds, mode)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -226,24 +242,34 @@ def kernel_microbench(torch, TwixTBatch, board_size, device, peak_gbs):
     bytes_unit = (2 * ((n * n + 7) // 8) + 16) + n * n
     out["legal_mask"] = {"envs_per_s": E / t, "ms": t * 1e3, "algo_bytes_per_env": bytes_unit,
                          "achieved_gbs": E * bytes_unit / t / 1e9, "frac": E * bytes_unit / t / 1e9 / peak_gbs}
-    # apply: one random legal move per env (first legal action of a random rotation), statuses on device
+    # apply: one random legal move per env (a random entry of its legal list), statuses on device; the records
+    # are restored from a device snapshot BEFORE each timed launch, and only the apply launch is bracketed
     idx = (torch.rand(E, device=dev) * cnts.clamp(min=1).float()).long().clamp(max=b.max_legal_actions - 1)
     move = acts.gather(1, idx.view(-1, 1)).view(-1).to(torch.int32)
     move = torch.where(cnts > 0, move, torch.full_like(move, -1))
     status = torch.zeros(E, dtype=torch.int32, device=dev)
     snap = torch.empty((E, b.record_words), dtype=torch.int32, device=dev)
     b.export_state(out=snap)
-
-    def apply_once():
+    b.set_validation(False)  # our own export: a plain device copy
+    ts = []
+    for rep in range(7):
         b.import_state(snap)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         b.apply(move, out_status=status)
-
-    t_both = timed(apply_once)
-    t_imp = timed(lambda: b.import_state(snap))
-    t = max(t_both - t_imp, 1e-9)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if rep >= 2:
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+    b.set_validation(True)
+    t = min(ts)
     out["apply"] = {"steps_per_s": E / t, "ms": t * 1e3, "algo_bytes_per_step": 2 * S,
                     "achieved_gbs": E * 2 * S / t / 1e9, "frac": E * 2 * S / t / 1e9 / peak_gbs,
-                    "illegal": int((status == 1).sum().item())}
+                    "illegal": int((status == 1).sum().item()), "timing": "CUDA events around the apply launch only"}
+    # import validation: one streaming pass over the records (validate kernel) + the device copy
+    t_val = timed(lambda: b.import_state(snap))
+    out["import_validated"] = {"envs_per_s": E / t_val, "ms": t_val * 1e3,
+                               "note": "validate kernel + device-to-device copy + 8-byte verdict read back"}
     b.close()
     del acts, mask, snap
     E4 = 1 << 16
@@ -255,8 +281,167 @@ def kernel_microbench(torch, TwixTBatch, board_size, device, peak_gbs):
     bytes_unit = S + 48 * n * (n - 2)
     out["observation"] = {"envs_per_s": E4 / t, "ms": t * 1e3, "algo_bytes_per_env": bytes_unit,
                           "achieved_gbs": E4 * bytes_unit / t / 1e9, "frac": E4 * bytes_unit / t / 1e9 / peak_gbs}
+    # BASELINE config C5: B = 65 536 mid-game states -> [B,12,n,n-2] f32 + [B,n*n] u8 by ONE launch
+    # (twixt_observation_and_mask through the torch / DLPack producer)
+    from twixt_for_open_spiel_b200.producer import ObservationMaskProducer
+    prod = ObservationMaskProducer(b)
+    t = timed(lambda: prod.produce())
+    bytes_unit = S + 48 * n * (n - 2) + n * n
+    out["obs_mask"] = {"envs_per_s": E4 / t, "ms": t * 1e3, "algo_bytes_per_env": bytes_unit, "batch": E4,
+                       "achieved_gbs": E4 * bytes_unit / t / 1e9, "frac": E4 * bytes_unit / t / 1e9 / peak_gbs,
+                       "workload": "BASELINE configs[4]: %d mid-game states, obs + legal mask in one pass" % E4}
+    del prod
     b.close()
     return out
+
+
+def other_configs(torch, TwixTBatch, device, args):
+    """BASELINE.json configs[0] (n = 8 playouts, the reference's default) and configs[2] (n = 12 MCTS leaf
+    rollouts, rollout_count = 4), each with the reference's CPU path on this host beside it."""
+    import numpy as np
+    from twixt_for_open_spiel_b200.rollout import BatchedRolloutEvaluator
+    dev = torch.device("cuda", device)
+    cores = _host_cores()
+    out = {}
+    # ---- C1: 1 Mi-env random playouts at n = 8
+    n, E = 8, 1 << 20
+    b = TwixTBatch(n, E, device, SEED)
+    b.use_torch_stream()
+    rets = torch.zeros((E, 2), dtype=torch.float32, device=dev)
+    lens = torch.zeros(E, dtype=torch.int32, device=dev)
+    ms = []
+    for i in range(3 + 5):
+        b.set_seed(SEED + i)
+        b.reset()
+        b.stats_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.playout(out_returns=rets, out_lengths=lens)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            ms.append(e0.elapsed_time(e1))
+    plies = b.stats()["plies"]
+    ids = np.arange(E, dtype=np.uint64)
+    rets_h, lens_h = np.zeros((E, 2), dtype=np.float32), np.zeros(E, dtype=np.int32)
+    b.reset()
+    b.playout(stream_ids=ids, out_returns=rets_h, out_lengths=lens_h)
+    t0 = time.perf_counter()
+    e2e_plies = 0
+    for i in range(3):
+        b.set_seed(SEED + 100 + i)
+        b.reset()
+        b.playout(stream_ids=ids, out_returns=rets_h, out_lengths=lens_h)
+        e2e_plies += int(lens_h.sum())
+    e2e_s = time.perf_counter() - t0
+    b.close()
+    med = statistics.median(ms)
+    c1 = {"workload": "twixt(board_size=8) %d-env random playouts to terminal (BASELINE.json configs[0])" % E,
+          "value": plies / (med * 1e-3), "unit": UNIT, "ms_per_launch": med, "plies_per_launch": plies,
+          "e2e": {"value": e2e_plies / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * 12}}
+    ref = None if args.no_cpu else cpu_reference_raw(8, cores, 3.0, "clone")
+    if ref is not None:
+        c1["cpu_baseline"] = {"value": ref["steps_per_sec"], "unit": UNIT, "cores": cores, "kind": "reference",
+                              "sample": "3 s of n=8 random playouts, %d processes, Clone() per game" % cores}
+    out["c1_n8"] = c1
+    # ---- C3: 4 096 leaves at a random ply in [0, 60] x 4 rollouts, n = 12
+    n, B, R = 12, 4096, 4
+    ev = BatchedRolloutEvaluator(n, n_rollouts=R, max_leaves=B, device=device, seed=SEED)
+    eb = ev.batch
+    for d in range(61):  # leaf e sits at ply ~ e*61/B: contiguous ranges of equal depth, made on the device
+        lo, hi = (d * B + 60) // 61, ((d + 1) * B + 60) // 61
+        if hi > lo and d > 0:
+            eb.playout(lo, hi - lo, max_plies=d, want_returns=False, want_lengths=False)
+    leaves = eb.export_state(0, B)
+    ev.evaluate_records(leaves)  # warm-up (staging buffers)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        host_means = ev.evaluate_records(leaves)
+    t_host = (time.perf_counter() - t0) / reps
+    eb.set_validation(False)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ev.evaluate_records(leaves)
+    t_trusted = (time.perf_counter() - t0) / reps
+    eb.set_validation(True)
+    eb.import_state(leaves, 0)
+    ev.evaluate_slots(B)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev_means = ev.evaluate_slots(B)
+    t_dev = (time.perf_counter() - t0) / reps
+    rec_bytes = int(leaves.nbytes)
+    c3 = {"workload": "twixt(board_size=12) %d MCTS leaves (ply 0..60) x %d random rollouts each, mean returns per leaf "
+                      "(BASELINE.json configs[2], mcts_example --rollout_count=4 shape)" % (B, R),
+          "value": B / t_host, "unit": "leaves/s", "rollouts_per_s": B * R / t_host, "ms_per_batch": t_host * 1e3,
+          "api": "BatchedRolloutEvaluator.evaluate_records(host records): validated import, device clone x4, ONE "
+                 "playout launch, returns to the host",
+          "h2d_bytes_per_batch": rec_bytes + B * R * 16, "d2h_bytes_per_batch": B * R * 8,
+          "trusted_import": {"value": B / t_trusted, "unit": "leaves/s", "ms_per_batch": t_trusted * 1e3},
+          "device_resident": {"value": B / t_dev, "unit": "leaves/s", "ms_per_batch": t_dev * 1e3,
+                              "api": "evaluate_slots: leaves already in env slots on the device; clone, playout and "
+                                     "the mean stay on the device", "h2d_bytes_per_batch": 0,
+                              "d2h_bytes_per_batch": B * 8},
+          "mean_abs_return": float(np.abs(host_means).mean()), "device_mean_abs_return": float(np.abs(dev_means).mean())}
+    ref = None if args.no_cpu else cpu_reference_raw(12, cores, 3.0, "rollout")
+    if ref is not None:
+        c3["cpu_baseline"] = {"value": ref["leaves_per_sec"], "unit": "leaves/s", "cores": cores, "kind": "reference",
+                              "sample": "3 s of the reference's rollout evaluation (4 x Clone + random playout per "
+                                        "leaf), %d processes" % cores}
+    ev.close()
+    out["c3_n12"] = c3
+    return out
+
+
+def adapter_latency(TwixTBatch, n, device, args):
+    """What ONE State method costs through the C ABI with count = 1 and host buffers (kernel launch + copy +
+    synchronise), i.e. the per-call price an unbatched open_spiel driver pays through the drop-in adapter,
+    beside the reference's own per-call time on this host (oracle/_ref/ref_bench latency)."""
+    import numpy as np
+    b = TwixTBatch(n, 8, device, SEED)
+    b.playout(0, 8, max_plies=150, want_returns=False, want_lengths=False)
+    acts = np.zeros((1, b.max_legal_actions), dtype=np.int64)
+    cnt = np.zeros(1, dtype=np.int32)
+    obs = np.zeros((1,) + b.obs_shape, dtype=np.float32)
+    term = np.zeros(1, dtype=np.uint8)
+    ret = np.zeros((1, 2), dtype=np.float32)
+
+    def per_call(fn, reps=400):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    res = {"board_size": n, "count": 1, "buffers": "host (pageable numpy)", "unit": "us per call",
+           "note": "through ctypes (about 1 us of the figure is the Python call itself)"}
+    res["legal_actions"] = per_call(lambda: b.legal_actions(0, 1, out_actions=acts, out_counts=cnt))
+    res["observation_tensor"] = per_call(lambda: b.observation(0, 1, out=obs))
+    res["is_terminal"] = per_call(lambda: b.is_terminal(0, 1, out=term))
+    res["returns"] = per_call(lambda: b.returns(0, 1, out=ret))
+    res["clone"] = per_call(lambda: b.clone(0, 1, 1))
+    # apply: a legal move each time (the state is restored by a device clone outside the timed call)
+    b.clone(0, 2, 1)
+    b.legal_actions(0, 1, out_actions=acts, out_counts=cnt)
+    move = np.array([acts[0, 0]], dtype=np.int32)
+    status = np.zeros(1, dtype=np.int32)
+    tot = 0.0
+    for i in range(220):
+        b.clone(2, 0, 1)
+        b.synchronize()
+        t0 = time.perf_counter()
+        b.apply(move, 0, out_status=status)
+        if i >= 20:
+            tot += time.perf_counter() - t0
+    res["apply_action"] = tot / 200 * 1e6
+    b.close()
+    ref = None if args.no_cpu else cpu_reference_raw(n, 1, 1.5, "latency")
+    if ref is not None:
+        res["reference_ns"] = {k: ref[k] for k in ("legal_actions_ns", "apply_action_ns", "observation_tensor_ns",
+                                                   "clone_ns", "is_terminal_returns_ns")}
+    return res
 
 
 def run_ours(args):
@@ -336,7 +521,7 @@ def run_ours(args):
     lens_host = torch.zeros(E, dtype=torch.int32).pin_memory()
     ids_np = ids_host.numpy().view(np.uint64)
     rets_np, lens_np = rets_host.numpy(), lens_host.numpy()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = args.steps  # the same number of steps as the device-timed arm
 
     def e2e_step(i):
         batch.set_seed(SEED + 1000 + i)
@@ -363,18 +548,37 @@ def run_ours(args):
         peak, peak_src = _peaks()
         plies_per_launch = st["plies"] / args.steps
         k_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = plies_per_launch * ALGO_BYTES_PER_STEP / (k_ms * 1e-3) / 1e9
-        traffic = _traffic()
+        kernel_steps_per_s = plies_per_launch / (k_ms * 1e-3)
+        conv = plies_per_launch * ALGO_BYTES_PER_STEP / (k_ms * 1e-3) / 1e9
+        cap = _playout_capture()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        f_sm = 1e6 * float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965)
         roofline = {
-            "bound": "hbm", "kernel": "playout_kernel<24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
-            "peak_source": peak_src + " (burst copy figure)",
-            "algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP, "steps_per_launch": plies_per_launch,
+            "bound": "issue", "kernel": "playout_kernel<24>", "unit": "steps/s", "achieved": kernel_steps_per_s,
             "kernel_ms": k_ms, "kernel_ms_median": statistics.median(kernel_ms), "kernel_ms_best": min(kernel_ms),
-            "note": "convention of SURVEY 8(d): state streamed once per move; the kernel keeps state on chip, "
-                    "true DRAM traffic is ~2 records per GAME, so frac>1 is expected and the real limiter is "
-                    "issue slots / shared memory (see profiles/)",
+            "steps_per_launch": plies_per_launch,
+            "ceiling": "SMs x 4 schedulers x f_SM x 32 lanes / thread-instructions per ply: every issue slot used, "
+                       "every lane active, at this build's instruction count",
+            # what the HBM convention of SURVEY 8(d) gives for the same launch (state streamed once per MOVE;
+            # the kernel streams it once per GAME, so this is not a physical fraction)
+            "hbm_convention": {"achieved_gbs": conv, "peak_gbs": peak, "frac": conv / peak,
+                               "algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP, "peak_source": peak_src},
         }
+        if cap is not None:
+            tipp = cap["thread_inst_per_launch"] / cap["plies_per_launch"]
+            ceiling = sms * 4 * f_sm * 32 / tipp
+            roofline.update({
+                "peak": ceiling, "frac": kernel_steps_per_s / ceiling, "thread_inst_per_ply": tipp,
+                "sm_count": sms, "f_sm_hz": f_sm,
+                "traffic": cap["dram_bytes_per_launch"],
+                "dram_frac_of_measured_peak": cap["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9 / peak,
+                "ncu": {k: cap[k] for k in ("source", "warp_inst_per_launch", "lanes_per_warp_inst", "issue_active_pct",
+                                            "alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct", "warps_per_sm",
+                                            "registers", "duration_ms") if k in cap},
+            })
+        else:
+            roofline.update({"peak": None, "frac": None, "traffic": None,
+                             "note": "profiles/r2_playout_ncu.json (ncu capture of this build) is missing"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True,
@@ -408,6 +612,9 @@ def run_ours(args):
                 "faithful_value": faithful}
         if world == 1 and not args.no_kernels:
             line["kernels"] = kernel_microbench(torch, TwixTBatch, n, local, peak)
+        if world == 1 and not args.no_configs:
+            line["configs"] = other_configs(torch, TwixTBatch, local, args)
+            line["adapter_latency_us"] = adapter_latency(TwixTBatch, n, local, args)
         print(json.dumps(line))
     batch.close()
     if world > 1:
@@ -428,6 +635,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=3.0, help="CPU sample per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs c1_n8 / c3_n12 and adapter_latency_us")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

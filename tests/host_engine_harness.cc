@@ -81,7 +81,8 @@ struct SmemRec {
 };
 
 // The same playout with the structure of the CUDA kernel: per-column count cache, moves interleaved with
-// single flood visits (a visit takes a whole stack entry; a new flood starts from the peg itself), two
+// single flood visits (a visit takes a whole stack entry; a new flood starts from the peg itself; the
+// opponent keeps moving while a colour's flood is still running), two
 // buffered Philox blocks refreshed on a fixed 4-iteration schedule, the selection of move i+1 issued
 // (speculatively) between the placement and the link evaluation of move i, and the swap's first half run
 // ahead of the move in the rare-events step.
@@ -98,7 +99,7 @@ int playout_like_kernel(B& b, Header& h, int n, uint64_t seed, uint64_t stream, 
     const uint32_t rel = index - 4u * rq;
     return rel < 4u ? ra[rel] : rb[rel - 4u];
   };
-  uint32_t pend = 0, origin = 0;
+  uint32_t pend = 0, origin_r = 0, origin_b = 0, fcol = 0;  // per-colour flood bookkeeping, as in the kernel
   int fplane = P_START;
   LocalStack<TW_TEST_STACK> stk;
   bool playing = h.result == kOpen && max_plies > 0;
@@ -116,7 +117,9 @@ int playout_like_kernel(B& b, Header& h, int n, uint64_t seed, uint64_t stream, 
       swap_first_move(b, h, sx, sy);
       swap_next = false;
     }
-    if (playing && pend == 0u && stk.empty()) {
+    const uint32_t mover = h.ply & 1u;
+    const bool flood_blocks = ((pend >> (2u * mover)) & 3u) != 0u || (!stk.empty() && fcol == mover);
+    if (playing && !flood_blocks) {
       if (actions_out) actions_out[step] = sact;
       const Placement pl = begin_move<true>(b, h, sx, sy);
       Header hn = h;  // the position the following move is chosen in, if this move does not end the game
@@ -124,9 +127,11 @@ int playout_like_kernel(B& b, Header& h, int n, uint64_t seed, uint64_t stream, 
       const int ln = legal_count(hn, n);
       int nx, ny;
       select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
-      const bool win = link_move<true>(b, pl, pend);
+      uint32_t owed;
+      const bool win = link_move<true>(b, pl, owed);
       finish_move(h, pl, win);
-      origin = flood_entry(pl.x, 1u << pl.y);
+      pend |= owed << (2 * pl.player);
+      (pl.player == kRed ? origin_r : origin_b) = flood_entry(pl.x, 1u << pl.y);
       ++step;
       playing = h.result == kOpen && step < max_plies;
       sx = nx;
@@ -136,13 +141,16 @@ int playout_like_kernel(B& b, Header& h, int n, uint64_t seed, uint64_t stream, 
     }
     if (!stk.empty() || pend != 0u) {
       const bool begin = stk.empty();
-      const bool start = (pend & kFloodStart) != 0u;
+      const uint32_t next_mover = h.ply & 1u;
+      const uint32_t col = ((pend >> (2u * next_mover)) & 3u) != 0u ? next_mover : (next_mover ^ 1u);
+      const bool start = ((pend >> (2u * col)) & kFloodStart) != 0u;
       fplane = begin ? (start ? P_START : P_END) : fplane;
-      pend &= begin ? (start ? ~kFloodStart : ~kFloodEnd) : ~0u;
-      const uint32_t e = stk.top_or(origin);
+      fcol = begin ? col : fcol;
+      pend &= begin ? ~((start ? kFloodStart : kFloodEnd) << (2u * col)) : ~0u;
+      const uint32_t e = stk.top_or(col == kRed ? origin_r : origin_b);
       flood_visit_entry(b, fplane, stk, e);
       if (stk.empty() && stk.overflow) {
-        flood_closure(b, ((h.ply - 1u) & 1u) == kRed ? P_RED : P_BLUE, fplane);
+        flood_closure(b, fcol == kRed ? P_RED : P_BLUE, fplane);
         stk.overflow = false;
       }
     }

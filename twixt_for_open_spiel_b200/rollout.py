@@ -55,6 +55,28 @@ class BatchedRolloutEvaluator:
         self._calls += 1
         return rets.reshape(num, r, 2).mean(axis=1, dtype=np.float64).astype(np.float32)
 
+    def evaluate_slots(self, num_leaves: int, max_plies: Optional[int] = None) -> np.ndarray:
+        """Device-resident form: the leaves already live in slots [0, num_leaves) of `self.batch` (put there by
+        twixt_apply / twixt_replay / twixt_clone_from on the device), so nothing but the [B, 2] means crosses
+        the bus: clone x R on the device, one playout launch, the mean over the rollouts on the device."""
+        import torch
+        if num_leaves > self.max_leaves:
+            raise ValueError("%d leaves > max_leaves %d" % (num_leaves, self.max_leaves))
+        b, r = self._batch, self.n_rollouts
+        dev = torch.device("cuda", b.device)
+        if getattr(self, "_dev_src", None) is None:
+            b.use_torch_stream()
+            self._dev_src = torch.arange(self.max_leaves, dtype=torch.int64, device=dev).repeat_interleave(r)
+            self._dev_rets = torch.empty((self.max_leaves * r, 2), dtype=torch.float32, device=dev)
+            self._dev_ids = torch.empty(self.max_leaves * r, dtype=torch.int64, device=dev)
+        n = num_leaves * r
+        self._dev_ids[:n] = torch.arange(n, dtype=torch.int64, device=dev) + self._calls * self.max_leaves * r
+        b.clone_gather(self._dev_src[:n], self.max_leaves)
+        b.playout(self.max_leaves, n, max_plies=max_plies, stream_ids=self._dev_ids[:n],
+                  out_returns=self._dev_rets[:n], want_lengths=False)
+        self._calls += 1
+        return self._dev_rets[:n].view(num_leaves, r, 2).double().mean(dim=1).float().cpu().numpy()
+
     def evaluate(self, states: Sequence[TwixTState]) -> np.ndarray:
         """RandomRolloutEvaluator::Evaluate for a list of adapter states."""
         return self.evaluate_records(np.stack([s.export_record() for s in states]))
