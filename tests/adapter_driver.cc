@@ -8,6 +8,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "twixt_b200_game.h"
@@ -160,6 +161,52 @@ static int DrawTest() {  // twixt_test.cc:185-199
   return 0;
 }
 
+// States of ONE shared game used from several threads at once (what AlphaZero actors / parallel MCTS do):
+// every thread replays the same fixed games on its own States and must see exactly the legal lists, tensors
+// and strings the single-threaded run saw.  All these States share one device batch -- the adapter serialises
+// the calls into it (EnvPool, twixt_b200_game.h).
+static int ThreadsTest() {
+  auto game = Load(0);
+  const std::vector<std::vector<Action>> games = {{21, 38, 15, 11, 27, 17, 42, 45, 48}, {19, 19, 36, 21, 50, 13, 9}};
+  struct Seen {
+    std::vector<std::vector<Action>> legal;
+    std::vector<std::vector<float>> obs;
+    std::string last;
+  };
+  auto play = [&](const std::vector<Action>& acts) {
+    Seen s;
+    auto state = game->NewInitialState();
+    for (Action a : acts) {
+      s.legal.push_back(state->LegalActions());
+      std::vector<float> o(576);
+      state->ObservationTensor(0, absl::Span<float>(o.data(), o.size()));
+      s.obs.push_back(o);
+      auto copy = state->Clone();  // clones are made and dropped concurrently too
+      copy->ApplyAction(a);
+      state->ApplyAction(a);
+      if (copy->ToString() != state->ToString()) s.last = "clone differs";
+    }
+    if (s.last.empty()) s.last = state->ToString();
+    return s;
+  };
+  std::vector<Seen> want;
+  for (const auto& g : games) want.push_back(play(g));
+  const int kThreads = 8, kRounds = 6;
+  std::vector<int> bad(kThreads, 0);
+  std::vector<std::thread> threads;
+  for (int t = 0; t < kThreads; ++t)
+    threads.emplace_back([&, t]() {
+      for (int r = 0; r < kRounds; ++r) {
+        const size_t gi = static_cast<size_t>((t + r) % games.size());
+        Seen got = play(games[gi]);
+        if (got.legal != want[gi].legal || got.obs != want[gi].obs || got.last != want[gi].last) ++bad[t];
+      }
+    });
+  for (auto& th : threads) th.join();
+  for (int t = 0; t < kThreads; ++t) EXPECT(bad[t] == 0);
+  return 0;
+}
+
 // CRC-32 (IEEE, as zlib.crc32) of a byte string
 static uint32_t Crc32(const std::string& s) {
   uint32_t c = 0xFFFFFFFFu;
@@ -261,7 +308,7 @@ int main(int argc, char** argv) {
       if (argc > 2 && RenderTest(argv[2]) != 0) return 1;
       if (argc > 3 && RenderRecordsTest(argv[3]) != 0) return 1;
     } else {
-      if (SwapTest() != 0 || LegalActionsTest() != 0 || DrawTest() != 0) return 1;
+      if (SwapTest() != 0 || LegalActionsTest() != 0 || DrawTest() != 0 || ThreadsTest() != 0) return 1;
       if (argc > 2 && StringsTest(argv[2]) != 0) return 1;
     }
   } catch (const std::exception& e) {

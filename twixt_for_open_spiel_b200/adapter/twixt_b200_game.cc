@@ -36,8 +36,11 @@ std::unique_ptr<Game> Factory(const GameParameters& params) {
 REGISTER_SPIEL_GAME(kGameType, Factory);
 
 void Check(int rc) {
-  if (rc != TWIXT_OK) SpielFatalError(twixt_last_error());
+  if (rc != TWIXT_OK) SpielFatalError(twixt_last_error());  // (thread-local text: read before the lock is dropped)
 }
+
+// Holds the mutex of a slot's batch for the duration of one twixt_* call (see EnvPool in the header).
+using BatchLock = std::lock_guard<std::mutex>;
 
 }  // namespace
 
@@ -55,7 +58,8 @@ EnvPool::Slot EnvPool::Take() {
     twixt_batch* b = nullptr;
     Check(twixt_create(board_size_, pool_size_, device_, /*seed=*/0, &b));
     batches_.push_back(b);
-    for (int64_t i = pool_size_ - 1; i >= 0; --i) free_.push_back({b, i});
+    batch_mu_.push_back(std::make_unique<std::mutex>());
+    for (int64_t i = pool_size_ - 1; i >= 0; --i) free_.push_back({b, i, batch_mu_.back().get()});
   }
   Slot s = free_.back();
   free_.pop_back();
@@ -82,31 +86,43 @@ const TwixTB200Game& TwixTB200State::parent() const { return static_cast<const T
 
 TwixTB200State::TwixTB200State(std::shared_ptr<const Game> game) : State(std::move(game)) {
   slot_ = parent().pool().Take();
+  BatchLock lock(*slot_.mu);
   Check(twixt_reset(slot_.batch, slot_.index, 1));
 }
 
 TwixTB200State::TwixTB200State(const TwixTB200State& other) : State(other) {
   slot_ = parent().pool().Take();
-  if (slot_.batch == other.slot_.batch) Check(twixt_clone(slot_.batch, other.slot_.index, slot_.index, 1));
-  else Check(twixt_clone_from(slot_.batch, slot_.index, other.slot_.batch, other.slot_.index, 1));
+  if (slot_.batch == other.slot_.batch) {
+    BatchLock lock(*slot_.mu);
+    Check(twixt_clone(slot_.batch, other.slot_.index, slot_.index, 1));
+  } else {
+    // two batches: both streams are involved (the copy waits for the source's pending work); std::lock
+    // takes the two mutexes without a lock-order deadlock
+    std::unique_lock<std::mutex> a(*slot_.mu, std::defer_lock), b(*other.slot_.mu, std::defer_lock);
+    std::lock(a, b);
+    Check(twixt_clone_from(slot_.batch, slot_.index, other.slot_.batch, other.slot_.index, 1));
+  }
 }
 
 TwixTB200State::~TwixTB200State() { parent().pool().Give(slot_); }
 
 Player TwixTB200State::CurrentPlayer() const {
   int8_t p = 0;
+  BatchLock lock(*slot_.mu);
   Check(twixt_current_player(slot_.batch, slot_.index, 1, &p));
   return p;  // -4 == kTerminalPlayerId when the game is over
 }
 
 bool TwixTB200State::IsTerminal() const {
   uint8_t t = 0;
+  BatchLock lock(*slot_.mu);
   Check(twixt_is_terminal(slot_.batch, slot_.index, 1, &t));
   return t != 0;
 }
 
 std::vector<double> TwixTB200State::Returns() const {
   float r[2] = {0.f, 0.f};
+  BatchLock lock(*slot_.mu);
   Check(twixt_returns(slot_.batch, slot_.index, 1, r));
   return {static_cast<double>(r[0]), static_cast<double>(r[1])};
 }
@@ -115,7 +131,10 @@ std::vector<Action> TwixTB200State::LegalActions() const {
   std::vector<Action> out(static_cast<size_t>(parent().board_size() * (parent().board_size() - 2)));
   int32_t count = 0;
   static_assert(sizeof(Action) == 8, "open_spiel::Action is int64");
-  Check(twixt_legal_actions(slot_.batch, slot_.index, 1, out.data(), 8, static_cast<int64_t>(out.size()), &count));
+  {
+    BatchLock lock(*slot_.mu);
+    Check(twixt_legal_actions(slot_.batch, slot_.index, 1, out.data(), 8, static_cast<int64_t>(out.size()), &count));
+  }
   out.resize(static_cast<size_t>(count));
   return out;
 }
@@ -123,6 +142,7 @@ std::vector<Action> TwixTB200State::LegalActions() const {
 void TwixTB200State::DoApplyAction(Action action) {
   if (action < 0 || action > INT32_MAX) SpielFatalError("Not a legal action: " + std::to_string(action));
   const int32_t a = static_cast<int32_t>(action);
+  BatchLock lock(*slot_.mu);
   Check(twixt_apply(slot_.batch, slot_.index, 1, &a, nullptr));  // "Not a legal action: N" (twixt.h:96)
 }
 
@@ -131,6 +151,7 @@ void TwixTB200State::ObservationTensor(Player player, absl::Span<float> values) 
   SPIEL_CHECK_LT(player, kNumPlayers);
   const int n = parent().board_size();
   SPIEL_CHECK_EQ(static_cast<int>(values.size()), TWIXT_NUM_OBS_PLANES * n * (n - 2));
+  BatchLock lock(*slot_.mu);
   Check(twixt_observation(slot_.batch, slot_.index, 1, values.data()));
 }
 
@@ -150,7 +171,10 @@ std::string TwixTB200State::ToString() const {
   twixt_game_info info;
   Check(twixt_get_info(slot_.batch, &info));
   std::vector<uint32_t> rec(static_cast<size_t>(info.record_words));
-  Check(twixt_export_state(slot_.batch, slot_.index, 1, rec.data()));
+  {
+    BatchLock lock(*slot_.mu);
+    Check(twixt_export_state(slot_.batch, slot_.index, 1, rec.data()));
+  }
   return RenderRecord(rec.data(), parent().board_size(), parent().ansi_color_output());
 }
 

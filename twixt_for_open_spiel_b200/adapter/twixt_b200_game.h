@@ -35,6 +35,13 @@ inline constexpr int kDefaultPoolSize = 256;
 class TwixTB200Game;
 
 // Env slots of one game, grown a batch at a time.
+//
+// THREAD SAFETY.  open_spiel callers (AlphaZero actors, parallel MCTS) use States of one shared Game from
+// several threads, while a twixt_batch is not thread-safe (include/twixt_b200.h: it owns one stream, one
+// set of staging buffers and one error slot).  Up to pool_size States share a batch, so every twixt_* call a
+// State makes is serialised on that batch's mutex (BatchLock below); the free list has its own.  Guarantee:
+// distinct States may be used concurrently from different threads, one State from one thread at a time --
+// the same contract as the reference's State objects.  Calls on States of different batches do not contend.
 class EnvPool {
  public:
   EnvPool(int board_size, int device, int pool_size);
@@ -42,6 +49,7 @@ class EnvPool {
   struct Slot {
     twixt_batch* batch;
     int64_t index;
+    std::mutex* mu;  // serialises all calls into `batch`
   };
   Slot Take();
   void Give(Slot s);
@@ -50,6 +58,7 @@ class EnvPool {
   int board_size_, device_, pool_size_;
   std::mutex mu_;
   std::vector<twixt_batch*> batches_;
+  std::vector<std::unique_ptr<std::mutex>> batch_mu_;
   std::vector<Slot> free_;
 };
 
