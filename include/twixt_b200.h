@@ -28,7 +28,7 @@
  *    is present.
  *
  * State record (what twixt_export_state / twixt_import_state move, and what
- * lives in HBM): per env `record_words` 32-bit words, 16-byte aligned:
+ * lives in HBM): per env `record_words` 32-bit words, a whole number of 128-byte lines:
  *    word 0  ply            (Board::move_counter_, twixtboard.h:75)
  *    word 1  bits 0-1 result (0 open 1 red won 2 blue won 3 draw, twixtboard.h:48)
  *            bit 2 swapped   (twixtboard.h:76)
@@ -44,7 +44,7 @@
  *            (Cell::linked_to_border_, twixtcell.h:89-95,107)
  *      8 peg has a blocked neighbour in an east direction
  *            (Cell::HasBlockedNeighborsEast, twixtcell.h:82-84)
- *    padding up to a multiple of 4 words.
+ *    zero padding up to a multiple of 32 words (n = 24: 224 words = 896 bytes).
  */
 #ifndef TWIXT_B200_H_
 #define TWIXT_B200_H_

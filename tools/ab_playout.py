@@ -63,6 +63,30 @@ def child(n, envs, reps):
         bad, ms[0], ms[len(ms) // 2], plies, plies / ms[len(ms) // 2] / 1e6))
 
 
+def child_kernels():
+    """the per-call kernels (bench.py's kernel section) with the library of this process"""
+    import json
+    import torch
+    import bench
+    from twixt_for_open_spiel_b200 import TwixTBatch
+    peak, _ = bench._peaks()
+    res = bench.kernel_microbench(torch, TwixTBatch, 24, 0, peak)
+    print("RESULT " + json.dumps({k: {"ms": round(v["ms"], 4), "frac": round(v.get("frac", 0.0), 4)} for k, v in res.items()}))
+
+
+def run_kernels():
+    names = ["<product>"] + sorted(f for f in os.listdir(VDIR) if f.endswith(".so"))
+    for rnd in range(2):
+        for name in names:
+            env = dict(os.environ)
+            if name != "<product>":
+                env["TWIXT_B200_LIB"] = os.path.join(VDIR, name)
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "child_kernels"], capture_output=True,
+                                 text=True, env=env)
+            line = [l for l in res.stdout.splitlines() if l.startswith("RESULT")]
+            print("%-24s round %d  %s" % (name, rnd, line[0] if line else "FAILED: " + res.stderr[-600:]), flush=True)
+
+
 def run(n, envs, reps):
     names = sorted(f for f in os.listdir(VDIR) if f.endswith(".so"))
     for rnd in range(2):  # two rounds, so that a drifting clock shows up as a difference between rounds
@@ -77,6 +101,10 @@ def run(n, envs, reps):
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build(sys.argv[2:])
+    elif sys.argv[1] == "child_kernels":
+        child_kernels()
+    elif sys.argv[1] == "kernels":
+        run_kernels()
     elif sys.argv[1] == "child":
         child(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     else:

@@ -38,7 +38,9 @@ for _ in range(3):
 r = TwixTBatch(n, E4, 0, 0x7477697854)
 r.use_torch_stream()
 _, _, trace = r.playout(max_plies=200, trace=True, want_returns=False, want_lengths=False)
-hist = torch.from_numpy(trace.astype("int32").T.copy()).to(dev)  # [E4, 200]
+hist_h = trace.astype("int32").T.copy()  # [E4, 200]
+hist_h[hist_h == 0xFFFF] = -1  # no move made (game over earlier): end of that history
+hist = torch.from_numpy(hist_h).to(dev)
 applied = torch.zeros(E4, dtype=torch.int32, device=dev)
 for _ in range(2):
     r.reset()

@@ -36,7 +36,10 @@ enum : int { kRed = 0, kBlue = 1 };
 enum : int { kTerminalPlayer = -4 };
 enum : uint32_t { kNoMove = 0xFFFFFFFFu };
 
-TW_HD int record_words(int n) { return (kHeaderWords + kNumStatePlanes * n + 3) & ~3; }
+// A record is padded to a whole number of 128-byte lines: the kernels that read only its head (header + the two
+// peg planes: legal list / mask, the first loads of apply) then pull whole lines of ONE record out of DRAM
+// instead of lines that straddle two (n = 24: 220 -> 224 words, +1.8 % memory; profiles/, K1 mask).
+TW_HD int record_words(int n) { return (kHeaderWords + kNumStatePlanes * n + 31) & ~31; }
 
 TW_HD int tw_popc(uint32_t v) {
 #if defined(__CUDA_ARCH__)

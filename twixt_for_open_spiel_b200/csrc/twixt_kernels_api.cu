@@ -448,31 +448,58 @@ __global__ void query_kernel(const uint32_t* __restrict__ records, int64_t count
 // stride over the envs; the NEXT env's record is fetched into registers while
 // the current one is expanded, so HBM latency hides behind the float stores.
 // Per env (all from shared memory):
-//  (1) the 12 planes as column words in BOARD coordinates (obs_plane_word);
-//  (2) one bit-word per OUTPUT row (GetTensorPosition, twixtboard.cc:590-597:
-//      red rows are board rows gathered across the column words, blue rows
-//      are one column word bit-reversed);
-//  (3) the rows concatenated into one flat bit stream of 12*n*(n-2) bits;
-//  (4) each thread turns 4 consecutive stream bits into a float4 (4 | 32, so a
-//      group never straddles a word) -- no index arithmetic beyond a shift.
-constexpr int kObsThreads = 256;
-constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
-constexpr int kObsStreamWords = (12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2) + 31) / 32;
-constexpr int kObsRecordWords = kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE;  // 220 <= 256 threads
-
+//  (A) the 12 planes as one bit word per OUTPUT row (GetTensorPosition,
+//      twixtboard.cc:590-597).  Red planes: output row r is board row n-1-r
+//      gathered across the column words -- a bit-matrix transpose, done by one
+//      warp per plane in registers (lane = column, five butterfly steps of
+//      shuffle + mask, instead of a 22-iteration bit loop per row).  Blue
+//      planes: output row r is ONE column word, bit-reversed.
+//  (B) the rows concatenated into one flat bit stream of 12*n*(n-2) bits;
+//  (C) each thread turns 4 consecutive stream bits into a float4 (4 | 32, so a
+//      group never straddles a word) by one 16-entry table look-up.
 //
 // kMask: the same pass also writes the env's [n*n] uint8 legal-action mask (upstream LegalActionsMask; the
 // AlphaZero-style producer of BASELINE config C5 wants both), so the record is read from HBM once for the
 // two outputs.  The mask is 576 of the 25 920 output bytes at n = 24.
+//
+// TW_OBS_BULK = 1 (an A/B variant): step (C) writes the floats into a double-buffered tile in
+// shared memory and ONE thread hands the whole 25 KB tile to the copy engine (cp.async.bulk shared -> global),
+// so the expansion of env i+1 overlaps the store of env i.
+#ifndef TW_OBS_BULK
+#define TW_OBS_BULK 0
+#endif
+constexpr int kObsThreads = 256;
+constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
+constexpr int kObsStreamWords = (12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2) + 31) / 32;
+constexpr int kObsRecordWords = (kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE + 31) & ~31;  // 224 <= 256 threads
+[[maybe_unused]] constexpr int kObsMaxFloats = 12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2);
+
+// 32 x 32 bit-matrix transpose across a warp: lane i holds row i on entry and column i on return.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t other = __shfl_xor_sync(kFullMask, x, j);
+    const bool upper = (lane & j) != 0;
+    const uint32_t lo = upper ? (other >> j) : x;   // what ends up under the mask
+    const uint32_t hi = upper ? x : (other << j);   // ... and outside it
+    x = (lo & m) | (hi & ~m);
+  }
+  return x;
+}
+
 template <bool kVec4, bool kMask>
-__global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t* __restrict__ records, int64_t count,
-                                                                  int n, int rw, float* __restrict__ out,
-                                                                  uint8_t* __restrict__ out_mask) {
-  __shared__ uint32_t legalw[TWIXT_MAX_BOARD_SIZE];               // kMask: legal cells per column
-  __shared__ __align__(16) uint32_t rec[kObsRecordWords + 4];  // the env's record
-  __shared__ uint32_t planes[kObsPlaneWords];                  // [12][n] column words, board coordinates
-  __shared__ uint32_t rowbits[kObsPlaneWords];                 // [12][n] output rows, bit c = tensor column c
-  __shared__ uint32_t stream[kObsStreamWords];                 // the tensor as a bit stream, output order
+__global__ void __launch_bounds__(kObsThreads, TW_OBS_BULK ? 4 : 8) observation_kernel(
+    const uint32_t* __restrict__ records, int64_t count, int n, int rw, float* __restrict__ out,
+    uint8_t* __restrict__ out_mask) {
+  __shared__ __align__(16) uint32_t rec[kObsRecordWords];  // the env's record
+  __shared__ uint32_t rowbits[kObsPlaneWords];             // [12][n] output rows, bit c = tensor column c
+  __shared__ uint32_t stream[kObsStreamWords];             // the tensor as a bit stream, output order
+  __shared__ uint32_t legalw[TWIXT_MAX_BOARD_SIZE];        // kMask: legal cells per column
+  __shared__ __align__(16) float4 lut[16];                 // 4 stream bits -> 4 floats
+#if TW_OBS_BULK
+  extern __shared__ __align__(128) float tile[];           // [2][total] staged output, double-buffered
+#endif
   const int w = n - 2;
   const int rows = 12 * n;
   const int total = rows * w;
@@ -481,25 +508,56 @@ __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t
   // bit / w by multiply-shift: m = ceil(2^20 / w) is exact while x * (m*w - 2^20) < 2^20, i.e. for every
   // x < 6336 + 32 and w <= 22; x*m < 2^32 as well (host-checked exhaustively in tests/test_abi.py)
   const uint32_t m_row = ((1u << 20) + w - 1) / w;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 16)
+    lut[tid] = make_float4((tid & 1) ? 1.0f : 0.0f, (tid & 2) ? 1.0f : 0.0f, (tid & 4) ? 1.0f : 0.0f,
+                           (tid & 8) ? 1.0f : 0.0f);
   int64_t env = blockIdx.x;
   uint32_t pre = (env < count && tid < rw) ? __ldg(records + env * rw + tid) : 0u;
+#if TW_OBS_BULK
+  int buf = 0;
+#endif
   for (; env < count; env += gridDim.x) {
     if (tid < rw) rec[tid] = pre;
     __syncthreads();
     const int64_t next = env + gridDim.x;
     if (next < count && tid < rw) pre = __ldg(records + next * rw + tid);  // in flight during the expansion
     RecordRef<1> b{rec, n};
-    for (int t = tid; t < rows; t += kObsThreads) {
-      const int p = t / n;
-      planes[t] = obs_plane_word(b, p, t - p * n);
-    }
-    if (kMask && tid < n) {  // TwixTState::LegalActions (twixt.h:86-90) as a bit word per column
-      Header h;
-      unpack_header(rec[0], rec[1], rec[2], rec[3], h);
-      legalw[tid] = h.result != kOpen ? 0u : legal_word(b, h, tid);
+    // ---- (A) one bit word per output row
+    if (warp < 6) {
+      // red plane p = warp: lane = board column x; after the transpose lane = board row y, bit = column x
+      const uint32_t colw = lane < n ? obs_plane_word(b, warp, lane) : 0u;
+      const uint32_t roww = warp_transpose32(colw, lane);
+      if (lane < n) rowbits[warp * n + (n - 1 - lane)] = (roww >> 1) & wmask;  // (r, c) <- cell (c+1, n-1-r)
+    } else {
+      // blue planes: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column word, reversed
+      for (int t = tid - 6 * 32; t < 6 * n; t += 2 * 32) {
+        const int p = t / n, x = t - p * n;
+        rowbits[(6 + p) * n + (n - 1 - x)] = (__brev(obs_plane_word(b, 6 + p, x)) >> (32 - (n - 1))) & wmask;
+      }
+      if (kMask && tid >= kObsThreads - 32 && lane < n) {  // TwixTState::LegalActions (twixt.h:86-90) as a bit word per column
+        Header h;
+        unpack_header(rec[0], rec[1], rec[2], rec[3], h);
+        legalw[lane] = h.result != kOpen ? 0u : legal_word(b, h, lane);
+      }
     }
     __syncthreads();
+    // ---- (B) the flat bit stream (+ the legal mask)
+    for (int k = tid; k < stream_words; k += kObsThreads) {
+      // stream bits [32k, 32k+32): the tail of one row and the heads of the following ones
+      const int bit0 = k << 5;
+      int row = static_cast<int>((static_cast<uint32_t>(bit0) * m_row) >> 20);
+      int have = 0;
+      uint32_t acc = 0;
+      int off = bit0 - row * w;  // bits of `row` already consumed by earlier words
+      while (have < 32 && row < rows) {
+        acc |= (rowbits[row] >> off) << have;
+        have += w - off;
+        off = 0;
+        ++row;
+      }
+      stream[k] = acc;
+    }
     if (kMask) {
       const int cells = n * n;
       uint8_t* mdst = out_mask + env * static_cast<int64_t>(cells);
@@ -521,50 +579,41 @@ __global__ void __launch_bounds__(kObsThreads) observation_kernel(const uint32_t
         }
       }
     }
-    for (int t = tid; t < rows; t += kObsThreads) {
-      const int p = t / n, r = t - p * n;
-      uint32_t bits = 0;
-      if (p < 6) {  // red: (r, c) <- cell (c+1, n-1-r)
-        const int y = n - 1 - r;
-        for (int c = 0; c < w; ++c) bits |= ((planes[p * n + c + 1] >> y) & 1u) << c;
-      } else {      // blue: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column, reversed
-        bits = (__brev(planes[p * n + (n - 1 - r)]) >> (32 - (n - 1))) & wmask;
-      }
-      rowbits[t] = bits;
-    }
     __syncthreads();
-    for (int k = tid; k < stream_words; k += kObsThreads) {
-      // stream bits [32k, 32k+32): the tail of one row and the heads of the following ones
-      const int bit0 = k << 5;
-      int row = static_cast<int>((static_cast<uint32_t>(bit0) * m_row) >> 20);
-      int have = 0;
-      uint32_t acc = 0;
-      int off = bit0 - row * w;  // bits of `row` already consumed by earlier words
-      while (have < 32 && row < rows) {
-        acc |= (rowbits[row] >> off) << have;
-        have += w - off;
-        off = 0;
-        ++row;
-      }
-      stream[k] = acc;
-    }
-    __syncthreads();
+    // ---- (C) bits -> floats
     float* dst = out + env * static_cast<int64_t>(total);
+#if TW_OBS_BULK
     if (kVec4) {
-      for (int q = tid; q < (total >> 2); q += kObsThreads) {  // total % 4 == 0
-        const uint32_t b4 = stream[q >> 3] >> ((q & 7) << 2);
-        float4 v;
-        v.x = (b4 & 1u) ? 1.0f : 0.0f;
-        v.y = (b4 & 2u) ? 1.0f : 0.0f;
-        v.z = (b4 & 4u) ? 1.0f : 0.0f;
-        v.w = (b4 & 8u) ? 1.0f : 0.0f;
-        reinterpret_cast<float4*>(dst)[q] = v;
+      // the copy engine may still be READING this buffer for the env two iterations back
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+      float4* t4 = reinterpret_cast<float4*>(tile + buf * kObsMaxFloats);
+      for (int q = tid; q < (total >> 2); q += kObsThreads)
+        t4[q] = lut[(stream[q >> 3] >> ((q & 7) << 2)) & 15u];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(t4));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                     "r"(static_cast<uint32_t>(total * 4))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      buf ^= 1;
+      continue;
+    }
+#endif
+    if (kVec4) {
+      for (int q = tid; q < (total >> 2); q += kObsThreads)  // total % 4 == 0
+        reinterpret_cast<float4*>(dst)[q] = lut[(stream[q >> 3] >> ((q & 7) << 2)) & 15u];
     } else {
       for (int j = tid; j < total; j += kObsThreads) dst[j] = ((stream[j >> 5] >> (j & 31)) & 1u) ? 1.0f : 0.0f;
     }
-    // the next iteration's first barrier orders these reads before rec/planes/rowbits/stream are rewritten
+    // the next iteration's first barrier orders these reads before rec/rowbits/stream are rewritten
   }
+#if TW_OBS_BULK
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the tiles must outlive their copies
+#endif
 }
 
 inline int grid_for(int64_t items, int threads, int max_blocks = 148 * 64) {
@@ -703,7 +752,17 @@ cudaError_t launch_observation(const uint32_t* records, int64_t count, int n, fl
   const int rw = record_words(n);
   const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const auto go = [&](auto k) {
+#if TW_OBS_BULK
+    const size_t tile_bytes = 2 * static_cast<size_t>(kObsMaxFloats) * sizeof(float);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_bytes));
+    int dev = 0, sms = 148, per_sm = 1;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kObsThreads, tile_bytes) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    k<<<grid_for(count, 1, sms * per_sm), kObsThreads, tile_bytes, s>>>(records, count, n, rw, out, out_mask);
+#else
     k<<<persistent_grid(k, kObsThreads, 1, count), kObsThreads, 0, s>>>(records, count, n, rw, out, out_mask);
+#endif
   };
   if (out_mask != nullptr) {
     if (vec) go(observation_kernel<true, true>);
