@@ -395,9 +395,11 @@ def other_configs(torch, TwixTBatch, device, args):
 
 
 def adapter_latency(TwixTBatch, n, device, args):
-    """What ONE State method costs through the C ABI with count = 1 and host buffers (kernel launch + copy +
-    synchronise), i.e. the per-call price an unbatched open_spiel driver pays through the drop-in adapter,
-    beside the reference's own per-call time on this host (oracle/_ref/ref_bench latency)."""
+    """What ONE State method costs through the C ABI with count = 1 and host buffers (kernel launch +
+    synchronise; small host transfers go through the pinned, device-mapped arena), i.e. the per-call price an
+    unbatched open_spiel driver pays, beside the reference's own per-call time on this host
+    (oracle/_ref/ref_bench latency).  The adapters do not make the four query calls per move: they call
+    twixt_step once per ApplyAction and keep its answer (`step_apply_and_query`)."""
     import numpy as np
     b = TwixTBatch(n, 8, device, SEED)
     b.playout(0, 8, max_plies=150, want_returns=False, want_lengths=False)
@@ -436,6 +438,18 @@ def adapter_latency(TwixTBatch, n, device, args):
         if i >= 20:
             tot += time.perf_counter() - t0
     res["apply_action"] = tot / 200 * 1e6
+    # twixt_step: ApplyAction + IsTerminal + CurrentPlayer + Returns + LegalActions of the new state in ONE launch
+    # (what the adapters call per move; the four queries are then served from the host)
+    legal = np.empty(b.max_legal_actions, dtype=np.int64)
+    tot = 0.0
+    for i in range(220):
+        b.clone(2, 0, 1)
+        b.synchronize()
+        t0 = time.perf_counter()
+        b.step(0, int(move[0]), out_legal=legal)
+        if i >= 20:
+            tot += time.perf_counter() - t0
+    res["step_apply_and_query"] = tot / 200 * 1e6
     b.close()
     ref = None if args.no_cpu else cpu_reference_raw(n, 1, 1.5, "latency")
     if ref is not None:

@@ -20,15 +20,17 @@
  *  - Every data pointer may be a DEVICE pointer (cudaMalloc / torch CUDA
  *    tensor: the kernel reads/writes it directly, asynchronously on the
  *    batch's stream) or a HOST pointer (pageable or pinned: the library stages
- *    it through device scratch and the call returns after the copy finished).
- *    The kind is detected with cudaPointerGetAttributes.
+ *    it -- small transfers through a pinned, device-mapped arena the kernel
+ *    accesses directly, large ones through device scratch -- and the call
+ *    returns after the data arrived).  The kind is detected with
+ *    cudaPointerGetAttributes.
  *  - A batch is not thread-safe; distinct batches are independent.
  *  - There is no CPU fallback: every entry point that touches game state
  *    launches sm_100a kernels and fails with TWIXT_ECUDA when no such device
  *    is present.
  *
  * State record (what twixt_export_state / twixt_import_state move, and what
- * lives in HBM): per env `record_words` 32-bit words, a whole number of 128-byte lines:
+ * lives in HBM): per env `record_words` 32-bit words, 16-byte aligned:
  *    word 0  ply            (Board::move_counter_, twixtboard.h:75)
  *    word 1  bits 0-1 result (0 open 1 red won 2 blue won 3 draw, twixtboard.h:48)
  *            bit 2 swapped   (twixtboard.h:76)
@@ -44,7 +46,7 @@
  *            (Cell::linked_to_border_, twixtcell.h:89-95,107)
  *      8 peg has a blocked neighbour in an east direction
  *            (Cell::HasBlockedNeighborsEast, twixtcell.h:82-84)
- *    zero padding up to a multiple of 32 words (n = 24: 224 words = 896 bytes).
+ *    zero padding up to a multiple of 4 words.
  */
 #ifndef TWIXT_B200_H_
 #define TWIXT_B200_H_
@@ -191,6 +193,25 @@ int twixt_observation_and_mask(twixt_batch* b, int64_t first, int64_t count, flo
  * pointer is a host pointer; with device pointers throughout the call is asynchronous). */
 int twixt_replay(twixt_batch* b, int64_t first, int64_t count, const int32_t* actions, int64_t stride,
                  const int32_t* lengths, int32_t* out_applied);
+
+/* One State step for an UNBATCHED caller -- what upstream example.cc / mcts_example.cc do per move:
+ * ApplyAction, then IsTerminal / CurrentPlayer / Returns / LegalActions of the new state (twixt.h:38-104).
+ * One kernel launch does all of it for env `env`: `action` >= 0 is applied with the legality test of
+ * DoApplyAction (status 1 and TWIXT_EILLEGAL "Not a legal action: N" if illegal, env unchanged),
+ * TWIXT_STEP_QUERY applies nothing, TWIXT_STEP_RESET resets the env to the initial position first; then
+ * `out` and the ascending `out_legal` ([max_legal_actions] int64 = open_spiel::Action, nullable) describe the
+ * resulting state.  An adapter keeps the answer with its State object, so the four query methods cost no
+ * further GPU call until the next ApplyAction (twixt_for_open_spiel_b200/adapter). */
+#define TWIXT_STEP_QUERY (-1)
+#define TWIXT_STEP_RESET (-2)
+typedef struct twixt_step_result {
+  int32_t status;         /* 0 applied / nothing to apply, 1 illegal action */
+  int32_t current_player; /* 0, 1 or TWIXT_TERMINAL_PLAYER */
+  int32_t is_terminal;
+  int32_t num_legal;      /* entries written to out_legal (0 when terminal) */
+  float returns[2];
+} twixt_step_result;
+int twixt_step(twixt_batch* b, int64_t env, int32_t action, twixt_step_result* out, int64_t* out_legal);
 
 /* The random-playout loop of upstream example.cc / RandomRolloutEvaluator
  * (LegalActions -> uniform pick -> ApplyAction until IsTerminal), fused into

@@ -397,7 +397,7 @@ class RefState(_StateBase):
         n = self.n
         cells = self.export_cells().reshape(n, n, 4).astype(np.int64)  # [x, y, field]
         hdr = self.board_header()  # move_counter, swapped, result, move_one x, y
-        words = (4 + 9 * n + 31) // 32 * 32
+        words = (4 + 9 * n + 3) // 4 * 4
         rec = np.zeros(words, dtype=np.uint32)
         color, links, blocked, flags = (cells[:, :, k] for k in range(4))
         bit = (np.int64(1) << np.arange(n, dtype=np.int64))[None, :]  # bit y of a column word

@@ -376,7 +376,7 @@ void oracle_export_cells(const oracle_game* g, const oracle_state* s, int* out) 
 
 int oracle_record_words(const oracle_game* g) {
   int w = ORACLE_HEADER_WORDS + ORACLE_NUM_STATE_PLANES * g->n;
-  return (w + 31) & ~31;  /* padded to 128-byte lines, as include/twixt_b200.h says */
+  return (w + 3) & ~3;
 }
 
 /* The packed record of include/twixt_b200.h, derived from the cell arrays.

@@ -11,7 +11,7 @@ int main(void) {
   twixt_batch* b = NULL;
   int rc;
   if (twixt_game_info_for(24, &info) != TWIXT_OK) return 1;
-  if (info.num_distinct_actions != 576 || info.obs_size != 12 * 24 * 22 || info.record_words != 224) return 2;
+  if (info.num_distinct_actions != 576 || info.obs_size != 12 * 24 * 22 || info.record_words != 220) return 2;
   if (info.max_game_length != 573 || info.max_legal_actions != 528) return 3;
   if (twixt_game_info_for(30, &info) != TWIXT_EINVAL) return 4;
   if (strcmp(twixt_last_error(), "board_size out of range [5..24]: 30") != 0) return 5;

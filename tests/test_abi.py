@@ -48,7 +48,7 @@ def test_game_info_and_range_errors():
         assert info.max_game_length == n * n - 3
         assert list(info.obs_shape) == [12, n, n - 2] and info.obs_size == 12 * n * (n - 2)
         assert info.max_legal_actions == n * (n - 2)
-        assert info.record_words == (4 + 9 * n + 31) // 32 * 32  # whole 128-byte lines
+        assert info.record_words == (4 + 9 * n + 3) // 4 * 4
         assert (info.min_utility, info.max_utility, info.utility_sum) == (-1.0, 1.0, 0.0)
     for bad in (30, 3, 4, 25, -1):
         with pytest.raises(SpielFatalError) as e:

@@ -453,3 +453,38 @@ def test_deserialize_uses_device_replay(oracle_mod):
         assert again._pool.stats()["kernel_launches"] - launches0 <= 3  # reset + ONE replay launch, not 55 applies
     with pytest.raises(SpielFatalError, match=r"^Not a legal action: %d$" % acts[3]):
         game.deserialize_state("\n".join(str(a) for a in acts[:6] + [acts[3]]))
+
+
+# ------------------------------------------------------------------ single-state step ---
+@pytest.mark.parametrize("n", [5, 8, 13, 24])
+def test_step_apply_and_query_in_one_launch(oracle_mod, n):
+    """twixt_step: ApplyAction + CurrentPlayer / IsTerminal / Returns / LegalActions of the new state from one
+    launch (what the adapters call per move), against the oracle at every ply of games with swaps; reset and
+    query modes; an illegal action reports the reference's message and changes nothing."""
+    from twixt_for_open_spiel_b200 import SpielFatalError, TwixTBatch
+    og = oracle_mod.OracleGame(n)
+    rng = random.Random(700 + n)
+    batch = TwixTBatch(n, 4, 0, SEED)
+    for gi in range(6):
+        env = gi % 4
+        acts = random_game_actions(og, rng, force_swap=(gi % 2 == 0))
+        st = og.new_initial_state()
+        launches0 = batch.stats()["kernel_launches"]
+        status, player, term, rets, legal = batch.step(env, -2)  # TWIXT_STEP_RESET
+        assert (status, player, term, rets) == (0, 0, False, [0.0, 0.0]) and legal.tolist() == st.legal_actions()
+        for ply, a in enumerate(acts):
+            if ply == 3:  # an occupied cell: illegal, state and answers unchanged
+                before = batch.export_state(env, 1)
+                with pytest.raises(SpielFatalError, match=r"^Not a legal action: %d$" % acts[2]):
+                    batch.step(env, acts[2])
+                assert np.array_equal(batch.export_state(env, 1), before)
+                _, p2, t2, r2, l2 = batch.step(env, -1)  # TWIXT_STEP_QUERY
+                assert (p2, t2, r2, l2.tolist()) == (st.current_player(), st.is_terminal(), st.returns(), st.legal_actions())
+            status, player, term, rets, legal = batch.step(env, a)
+            st.apply_action(a)
+            assert status == 0 and player == st.current_player() and term == st.is_terminal(), (n, gi, ply)
+            assert rets == st.returns() and legal.tolist() == st.legal_actions(), (n, gi, ply)
+        assert term and player == -4 and len(legal) == 0
+        assert np.array_equal(batch.export_state(env, 1)[0], st.export_record())
+        assert batch.stats()["kernel_launches"] - launches0 == 1 + len(acts) + 2  # one launch per step, nothing else
+    batch.close()

@@ -29,6 +29,16 @@ class GameInfo(C.Structure):
     ]
 
 
+class StepResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32),
+        ("current_player", C.c_int32),
+        ("is_terminal", C.c_int32),
+        ("num_legal", C.c_int32),
+        ("returns", C.c_float * 2),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("plies", C.c_int64),
@@ -75,6 +85,7 @@ SYMBOLS = [
     ("twixt_playout", C.c_int, [_P, _I64, _I64, C.c_int32, _P, _P, _P, _P, C.c_int32]),
     ("twixt_export_state", C.c_int, [_P, _I64, _I64, _P]),
     ("twixt_import_state", C.c_int, [_P, _I64, _I64, _P]),
+    ("twixt_step", C.c_int, [_P, _I64, C.c_int32, C.POINTER(StepResult), _P]),
     ("twixt_set_validation", C.c_int, [_P, C.c_int]),
     ("twixt_shard_range", C.c_int, [_I64, C.c_int32, C.c_int32, C.POINTER(_I64), C.POINTER(_I64)]),
     ("twixt_stats_accumulate", C.c_int, [C.POINTER(Stats), C.POINTER(Stats)]),

@@ -86,15 +86,15 @@ const TwixTB200Game& TwixTB200State::parent() const { return static_cast<const T
 
 TwixTB200State::TwixTB200State(std::shared_ptr<const Game> game) : State(std::move(game)) {
   slot_ = parent().pool().Take();
-  BatchLock lock(*slot_.mu);
-  Check(twixt_reset(slot_.batch, slot_.index, 1));
+  Step(TWIXT_STEP_RESET);  // NewInitialState (twixt.h:118-120): reset + the initial position's answers, one launch
 }
 
-TwixTB200State::TwixTB200State(const TwixTB200State& other) : State(other) {
+TwixTB200State::TwixTB200State(const TwixTB200State& other)
+    : State(other), now_(other.now_), legal_(other.legal_) {
   slot_ = parent().pool().Take();
   if (slot_.batch == other.slot_.batch) {
     BatchLock lock(*slot_.mu);
-    Check(twixt_clone(slot_.batch, other.slot_.index, slot_.index, 1));
+    Check(twixt_clone(slot_.batch, other.slot_.index, slot_.index, 1));  // asynchronous: ordered on the batch's stream
   } else {
     // two batches: both streams are involved (the copy waits for the source's pending work); std::lock
     // takes the two mutexes without a lock-order deadlock
@@ -106,44 +106,33 @@ TwixTB200State::TwixTB200State(const TwixTB200State& other) : State(other) {
 
 TwixTB200State::~TwixTB200State() { parent().pool().Give(slot_); }
 
-Player TwixTB200State::CurrentPlayer() const {
-  int8_t p = 0;
-  BatchLock lock(*slot_.mu);
-  Check(twixt_current_player(slot_.batch, slot_.index, 1, &p));
-  return p;  // -4 == kTerminalPlayerId when the game is over
-}
-
-bool TwixTB200State::IsTerminal() const {
-  uint8_t t = 0;
-  BatchLock lock(*slot_.mu);
-  Check(twixt_is_terminal(slot_.batch, slot_.index, 1, &t));
-  return t != 0;
-}
-
-std::vector<double> TwixTB200State::Returns() const {
-  float r[2] = {0.f, 0.f};
-  BatchLock lock(*slot_.mu);
-  Check(twixt_returns(slot_.batch, slot_.index, 1, r));
-  return {static_cast<double>(r[0]), static_cast<double>(r[1])};
-}
-
-std::vector<Action> TwixTB200State::LegalActions() const {
-  std::vector<Action> out(static_cast<size_t>(parent().board_size() * (parent().board_size() - 2)));
-  int32_t count = 0;
+void TwixTB200State::Step(int32_t action) {
+  const int n = parent().board_size();
+  std::vector<Action> legal(static_cast<size_t>(n * (n - 2)));
+  twixt_step_result res;
   static_assert(sizeof(Action) == 8, "open_spiel::Action is int64");
   {
     BatchLock lock(*slot_.mu);
-    Check(twixt_legal_actions(slot_.batch, slot_.index, 1, out.data(), 8, static_cast<int64_t>(out.size()), &count));
+    Check(twixt_step(slot_.batch, slot_.index, action, &res, legal.data()));  // "Not a legal action: N" (twixt.h:96)
   }
-  out.resize(static_cast<size_t>(count));
-  return out;
+  legal.resize(static_cast<size_t>(res.num_legal));
+  now_ = res;
+  legal_ = std::move(legal);
 }
+
+Player TwixTB200State::CurrentPlayer() const { return now_.current_player; }  // -4 == kTerminalPlayerId when over
+
+bool TwixTB200State::IsTerminal() const { return now_.is_terminal != 0; }
+
+std::vector<double> TwixTB200State::Returns() const {
+  return {static_cast<double>(now_.returns[0]), static_cast<double>(now_.returns[1])};
+}
+
+std::vector<Action> TwixTB200State::LegalActions() const { return legal_; }
 
 void TwixTB200State::DoApplyAction(Action action) {
   if (action < 0 || action > INT32_MAX) SpielFatalError("Not a legal action: " + std::to_string(action));
-  const int32_t a = static_cast<int32_t>(action);
-  BatchLock lock(*slot_.mu);
-  Check(twixt_apply(slot_.batch, slot_.index, 1, &a, nullptr));  // "Not a legal action: N" (twixt.h:96)
+  Step(static_cast<int32_t>(action));
 }
 
 void TwixTB200State::ObservationTensor(Player player, absl::Span<float> values) const {

@@ -8,6 +8,12 @@
 // evaluation runs on the GPU.  One State = one env slot of a device pool owned
 // by the Game; Clone() is a device-side record copy.
 //
+// Per-call cost.  A State keeps the answer of the last twixt_step -- current player, terminal flag, returns
+// and the legal-action list of its position -- so ApplyAction is ONE kernel launch + one synchronisation and
+// CurrentPlayer / IsTerminal / Returns / LegalActions are served from the host without touching the GPU
+// (the loop of example.cc / mcts_example.cc calls all of them between two moves).  Clone() is an
+// asynchronous device copy plus a copy of that cached answer.  ObservationTensor and ToString read the env.
+//
 // To build inside an open_spiel checkout: copy this directory to
 // open_spiel/games/twixt_b200/, add twixt_b200_game.cc to GAME_SOURCES and link
 // libtwixt_b200.so.  Here it is compile- and run-tested
@@ -86,7 +92,10 @@ class TwixTB200State : public State {
 
  private:
   const TwixTB200Game& parent() const;
+  void Step(int32_t action);  // twixt_step: (reset | apply | nothing), then refresh the cached answer
   EnvPool::Slot slot_;
+  twixt_step_result now_;       // of the current position
+  std::vector<Action> legal_;   // ascending; empty when terminal (twixt.h:86-90)
 };
 
 class TwixTB200Game : public Game {

@@ -203,6 +203,19 @@ class TwixTBatch:
         self._check(rc)
         return out_status
 
+    def step(self, env: int, action: int = -1, out_legal=None):
+        """One State step for an unbatched caller (twixt_step): `action` >= 0 is applied (illegal ->
+        SpielFatalError "Not a legal action: N"), STEP_QUERY (-1) applies nothing, STEP_RESET (-2) resets the
+        env first; returns (status, current_player, is_terminal, returns [2], legal actions int64 ascending)
+        of the resulting state -- one kernel launch for everything the caller asks between two moves."""
+        if out_legal is None:
+            out_legal = np.empty(self.max_legal_actions, dtype=np.int64)
+        res = _lib.StepResult()
+        self._check(self._lib.twixt_step(self._h, int(env), int(action), C.byref(res),
+                                         _ptr(out_legal, _dt(np.int64, "int64"), self.max_legal_actions)))
+        return (int(res.status), int(res.current_player), bool(res.is_terminal), [float(res.returns[0]), float(res.returns[1])],
+                out_legal[:res.num_legal])
+
     def current_player(self, first: int = 0, count: Optional[int] = None, out=None):
         first, count = self._range(first, count)
         if out is None:

@@ -99,6 +99,7 @@ int fill_game_info(int n, twixt_game_info* out) {
 struct Staged {
   void* user = nullptr;     // what the caller passed
   void* dev = nullptr;      // what the kernel uses
+  void* pin = nullptr;      // host alias of `dev` when the small-transfer arena is used (see PinAlloc)
   size_t bytes = 0;
   bool host = false;
 };
@@ -111,6 +112,7 @@ class TwixTBatch {
     if (stream_ != nullptr) cudaStreamSynchronize(stream_);
     if (records_ != nullptr) cudaFree(records_);
     if (d_stats_ != nullptr) cudaFree(d_stats_);
+    if (pinned_ != nullptr) cudaFreeHost(pinned_);
     for (int k = 0; k < kSlots; ++k)
       if (slot_[k] != nullptr) cudaFree(slot_[k]);
     if (own_stream_ && stream_ != nullptr) cudaStreamDestroy(stream_);
@@ -149,6 +151,12 @@ class TwixTBatch {
                   static_cast<long long>(num_envs_), cudaGetErrorString(e));
     }
     TW_CUDA(cudaMalloc(&d_stats_, sizeof(DeviceStats)));
+    if (cudaHostAlloc(&pinned_, kPinBytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer(&pinned_dev_, pinned_, 0) != cudaSuccess) {
+      cudaGetLastError();  // no mapped memory on this system: every host transfer takes the staged path
+      if (pinned_ != nullptr) cudaFreeHost(pinned_);
+      pinned_ = pinned_dev_ = nullptr;
+    }
     TW_CUDA(cudaMemsetAsync(d_stats_, 0, sizeof(DeviceStats), stream_));
     TW_CUDA(playout_setup());
     return Reset(0, num_envs_);
@@ -172,6 +180,29 @@ class TwixTBatch {
   int Synchronize() {
     DeviceGuard g(device_);
     TW_CUDA(cudaStreamSynchronize(stream_));
+    return TWIXT_OK;
+  }
+
+  // One State step for an unbatched caller (see twixt_step in the header): apply (or reset, or nothing),
+  // then player / terminal / returns / ascending legal actions of the resulting state, by ONE kernel launch
+  // whose outputs land in the pinned arena.
+  int Step(int64_t env, int32_t action, twixt_step_result* out, int64_t* out_legal) {
+    TW_TRY(CheckRange(env, 1));
+    if (out == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
+    if (action < TWIXT_STEP_RESET) return fail(TWIXT_EINVAL, "action %d: use an action >= 0, TWIXT_STEP_QUERY or TWIXT_STEP_RESET", action);
+    DeviceGuard g(device_);
+    ScratchReset();
+    Staged res, legal;
+    TW_TRY(StageOut(out, sizeof(twixt_step_result), &res, false));
+    TW_TRY(StageOut(out_legal, static_cast<size_t>(n_) * (n_ - 2) * sizeof(int64_t), &legal, false));
+    TW_CUDA(launch_step(rec(env), n_, action, static_cast<twixt_step_result*>(res.dev), static_cast<int64_t*>(legal.dev),
+                        stream_));
+    launches_ += 1;
+    TW_TRY(Finish(&res));
+    TW_TRY(Finish(&legal));
+    if (!res.host && !legal.host) return TWIXT_OK;
+    TW_TRY(Sync());
+    if (res.host && out->status == 1) return fail(TWIXT_EILLEGAL, "Not a legal action: %d", action);  // twixt.h:96
     return TWIXT_OK;
   }
   void SetSeed(uint64_t seed) { seed_ = seed; }
@@ -226,7 +257,7 @@ class TwixTBatch {
     launches_ += 1;
     unsigned int bad = 0xFFFFFFFFu;
     TW_CUDA(cudaMemcpyAsync(&bad, &d_stats_->bad_clone_index, sizeof(bad), cudaMemcpyDeviceToHost, stream_));
-    TW_CUDA(cudaStreamSynchronize(stream_));
+    TW_TRY(Sync());
     if (bad != 0xFFFFFFFFu)
       return fail(TWIXT_EINVAL, "src_ids[%u] is out of range or lies in the destination range (that env was not copied)", bad);
     return TWIXT_OK;
@@ -293,17 +324,31 @@ class TwixTBatch {
     ScratchReset();
     Staged in, st;
     TW_TRY(StageIn(actions, static_cast<size_t>(count) * sizeof(int32_t), &in));
-    TW_TRY(StageOut(out_status, static_cast<size_t>(count) * sizeof(int32_t), &st, false));
-    TW_CUDA(cudaMemsetAsync(&d_stats_->illegal_index, 0xFF, sizeof(unsigned int), stream_));
+    const size_t status_bytes = static_cast<size_t>(count) * sizeof(int32_t);
+    if (out_status == nullptr) PinAlloc(status_bytes, &st);  // small batches: statuses into the arena, read below
+    else TW_TRY(StageOut(out_status, status_bytes, &st, false));
+    // Where the statuses end up in host-visible memory the first illegal action is found by reading them;
+    // otherwise the kernel's device-side flag is reset, and read back after the launch.
+    const bool scan_host = st.pin != nullptr;
+    if (!scan_host) TW_CUDA(cudaMemsetAsync(&d_stats_->illegal_index, 0xFF, sizeof(unsigned int), stream_));
     TW_CUDA(launch_apply(rec(first), count, n_, static_cast<const int32_t*>(in.dev), static_cast<int32_t*>(st.dev),
                          d_stats_, stream_));
     launches_ += 1;
     TW_TRY(Finish(&st));
     if (out_status != nullptr && !st.host) return TWIXT_OK;  // fully asynchronous: caller inspects the statuses
-    unsigned int bad = 0xFFFFFFFFu;
-    TW_CUDA(cudaMemcpyAsync(&bad, &d_stats_->illegal_index, sizeof(bad), cudaMemcpyDeviceToHost, stream_));
-    TW_CUDA(cudaStreamSynchronize(stream_));
-    if (bad != 0xFFFFFFFFu) {
+    int64_t bad = -1;
+    if (scan_host) {
+      TW_TRY(Sync());
+      const int32_t* seen = static_cast<const int32_t*>(st.pin);
+      for (int64_t i = 0; i < count && bad < 0; ++i)
+        if (seen[i] == 1) bad = i;
+    } else {
+      unsigned int flag = 0xFFFFFFFFu;
+      TW_CUDA(cudaMemcpyAsync(&flag, &d_stats_->illegal_index, sizeof(flag), cudaMemcpyDeviceToHost, stream_));
+      TW_TRY(Sync());
+      if (flag != 0xFFFFFFFFu) bad = flag;
+    }
+    if (bad >= 0) {
       int32_t a = 0;
       if (in.host) a = actions[bad];
       else TW_CUDA(cudaMemcpy(&a, actions + bad, sizeof(a), cudaMemcpyDeviceToHost));
@@ -327,7 +372,7 @@ class TwixTBatch {
     TW_TRY(Finish(&p));
     TW_TRY(Finish(&t));
     TW_TRY(Finish(&r));
-    if (p.host || t.host || r.host) TW_CUDA(cudaStreamSynchronize(stream_));
+    if (p.host || t.host || r.host) TW_TRY(Sync());
     return TWIXT_OK;
   }
 
@@ -369,7 +414,7 @@ class TwixTBatch {
     if (out_applied != nullptr && !ap.host && !in.host && !len.host) return TWIXT_OK;  // asynchronous: caller inspects out_applied
     unsigned long long bad = ~0ull;
     TW_CUDA(cudaMemcpyAsync(&bad, &d_stats_->replay_illegal, sizeof(bad), cudaMemcpyDeviceToHost, stream_));
-    TW_CUDA(cudaStreamSynchronize(stream_));
+    TW_TRY(Sync());
     if (bad != ~0ull)  // twixt.h:96, same text
       return fail(TWIXT_EILLEGAL, "Not a legal action: %d", static_cast<int>(static_cast<int32_t>(bad & 0xFFFFFFFFull)));
     return TWIXT_OK;
@@ -410,7 +455,7 @@ class TwixTBatch {
     TW_TRY(Finish(&ret));
     TW_TRY(Finish(&len));
     TW_TRY(Finish(&act));
-    if (ids.host || ret.host || len.host || act.host) TW_CUDA(cudaStreamSynchronize(stream_));
+    if (ids.host || ret.host || len.host || act.host) TW_TRY(Sync());
     return TWIXT_OK;
   }
 
@@ -419,10 +464,11 @@ class TwixTBatch {
     if (count == 0) return TWIXT_OK;
     if (out == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
     DeviceGuard g(device_);
+    ScratchReset();
     const bool dev = is_device_pointer(out);
     TW_CUDA(cudaMemcpyAsync(out, rec(first), static_cast<size_t>(count) * rw_ * sizeof(uint32_t), cudaMemcpyDefault,
                             stream_));
-    if (!dev) TW_CUDA(cudaStreamSynchronize(stream_));
+    if (!dev) TW_TRY(Sync());
     return TWIXT_OK;
   }
 
@@ -435,13 +481,13 @@ class TwixTBatch {
     if (in == nullptr) return fail(TWIXT_EINVAL, "null input pointer");
     DeviceGuard g(device_);
     const size_t bytes = static_cast<size_t>(count) * rw_ * sizeof(uint32_t);
+    ScratchReset();
     if (!validate_) {  // twixt_set_validation(b, 0): trusted records (e.g. our own exports)
       const bool dev = is_device_pointer(in);
       TW_CUDA(cudaMemcpyAsync(rec(first), in, bytes, cudaMemcpyDefault, stream_));
-      if (!dev) TW_CUDA(cudaStreamSynchronize(stream_));
+      if (!dev) TW_TRY(Sync());
       return TWIXT_OK;
     }
-    ScratchReset();
     Staged src;
     TW_TRY(StageIn(in, bytes, &src));
     TW_CUDA(cudaMemsetAsync(&d_stats_->invalid_code, 0xFF, sizeof(unsigned long long), stream_));
@@ -449,12 +495,12 @@ class TwixTBatch {
     launches_ += 1;
     unsigned long long code = ~0ull;
     TW_CUDA(cudaMemcpyAsync(&code, &d_stats_->invalid_code, sizeof(code), cudaMemcpyDeviceToHost, stream_));
-    TW_CUDA(cudaStreamSynchronize(stream_));
+    TW_TRY(Sync());
     if (code != ~0ull)
       return fail(TWIXT_EINVAL, "invalid state record at index %lld: %s", static_cast<long long>(code >> 8),
                   invalid_reason_text(static_cast<unsigned>(code & 0xFFull)));
     TW_CUDA(cudaMemcpyAsync(rec(first), src.dev, bytes, cudaMemcpyDeviceToDevice, stream_));
-    if (src.host) TW_CUDA(cudaStreamSynchronize(stream_));
+    if (src.host) TW_TRY(Sync());
     return TWIXT_OK;
   }
   void SetValidation(bool on) { validate_ = on; }
@@ -462,9 +508,10 @@ class TwixTBatch {
   int GetStats(twixt_stats* out) {
     if (out == nullptr) return fail(TWIXT_EINVAL, "null output pointer");
     DeviceGuard g(device_);
+    ScratchReset();
     DeviceStats h;
     TW_CUDA(cudaMemcpyAsync(&h, d_stats_, sizeof(h), cudaMemcpyDeviceToHost, stream_));
-    TW_CUDA(cudaStreamSynchronize(stream_));
+    TW_TRY(Sync());
     out->plies = static_cast<int64_t>(h.plies);
     out->games = static_cast<int64_t>(h.games);
     out->red_wins = static_cast<int64_t>(h.red_wins);
@@ -487,7 +534,33 @@ class TwixTBatch {
   uint32_t* rec(int64_t env) const { return records_ + env * rw_; }
 
   // ---- device staging for host-side buffers: a few grow-only slots ------
-  void ScratchReset() { next_slot_ = 0; }
+  void ScratchReset() {
+    next_slot_ = 0;
+    pin_off_ = 0;
+    num_pending_ = 0;
+  }
+
+  // Small host-side transfers (the count = 1 calls of a drop-in adapter: a status word, a 4 KB legal list, a
+  // 25 KB tensor) go through a pinned, device-mapped arena instead of a device slot + cudaMemcpyAsync: the
+  // kernel reads / writes the host memory directly and the call costs one launch and one stream
+  // synchronisation.  Returns false when the request does not fit (the caller then uses a device slot).
+  bool PinAlloc(size_t bytes, Staged* s) {
+    const size_t need = (bytes + 255) & ~static_cast<size_t>(255);
+    if (pinned_ == nullptr || bytes > kPinMaxTransfer || pin_off_ + need > kPinBytes || num_pending_ >= kMaxPending)
+      return false;
+    s->pin = static_cast<char*>(pinned_) + pin_off_;
+    s->dev = static_cast<char*>(pinned_dev_) + pin_off_;
+    pin_off_ += need;
+    return true;
+  }
+
+  // stream synchronisation + delivery of what kernels wrote into the pinned arena
+  int Sync() {
+    TW_CUDA(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < num_pending_; ++i) memcpy(pending_[i].user, pending_[i].pin, pending_[i].bytes);
+    num_pending_ = 0;
+    return TWIXT_OK;
+  }
 
   int SlotAlloc(size_t bytes, void** out) {
     if (next_slot_ >= kSlots) return fail(TWIXT_ENOMEM, "internal: out of staging slots");
@@ -515,6 +588,10 @@ class TwixTBatch {
     if (user == nullptr || bytes == 0) { s->dev = nullptr; s->host = false; return TWIXT_OK; }
     if (is_device_pointer(user)) { s->dev = s->user; s->host = false; return TWIXT_OK; }
     s->host = true;
+    if (PinAlloc(bytes, s)) {
+      memcpy(s->pin, user, bytes);  // visible to the kernel: written before its launch
+      return TWIXT_OK;
+    }
     TW_TRY(SlotAlloc(bytes, &s->dev));
     TW_CUDA(cudaMemcpyAsync(s->dev, user, bytes, cudaMemcpyHostToDevice, stream_));
     return TWIXT_OK;
@@ -526,19 +603,27 @@ class TwixTBatch {
     if (user == nullptr || bytes == 0) { s->dev = nullptr; s->host = false; return TWIXT_OK; }
     if (is_device_pointer(user)) { s->dev = user; s->host = false; return TWIXT_OK; }
     s->host = true;
+    if (PinAlloc(bytes, s)) {
+      if (preserve) memcpy(s->pin, user, bytes);
+      return TWIXT_OK;
+    }
     TW_TRY(SlotAlloc(bytes, &s->dev));
     if (preserve) TW_CUDA(cudaMemcpyAsync(s->dev, user, bytes, cudaMemcpyHostToDevice, stream_));
     return TWIXT_OK;
   }
 
   int Finish(Staged* s) {
+    if (s->host && s->pin != nullptr) {
+      pending_[num_pending_++] = {s->user, s->pin, s->bytes};  // copied out by Sync()
+      return TWIXT_OK;
+    }
     if (s->host && s->dev != nullptr)
       TW_CUDA(cudaMemcpyAsync(s->user, s->dev, s->bytes, cudaMemcpyDeviceToHost, stream_));
     return TWIXT_OK;
   }
 
   int SyncIfHost(const Staged& a, const Staged& b) {
-    if (a.host || b.host) TW_CUDA(cudaStreamSynchronize(stream_));
+    if (a.host || b.host) TW_TRY(Sync());
     return TWIXT_OK;
   }
 
@@ -553,6 +638,19 @@ class TwixTBatch {
   DeviceStats* d_stats_ = nullptr;
   cudaStream_t stream_ = nullptr;
   bool own_stream_ = false;
+  // pinned, device-mapped arena for small host transfers
+  static constexpr size_t kPinBytes = 256 * 1024, kPinMaxTransfer = 96 * 1024;
+  static constexpr int kMaxPending = 8;
+  struct Pending {
+    void* user;
+    void* pin;
+    size_t bytes;
+  };
+  void* pinned_ = nullptr;
+  void* pinned_dev_ = nullptr;
+  size_t pin_off_ = 0;
+  Pending pending_[kMaxPending];
+  int num_pending_ = 0;
   static constexpr int kSlots = 4;
   void* slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   size_t slot_cap_[kSlots] = {0, 0, 0, 0};
@@ -675,6 +773,10 @@ int twixt_replay(twixt_batch* b, int64_t first, int64_t count, const int32_t* ac
                  const int32_t* lengths, int32_t* out_applied) {
   TW_NEED(b);
   return b->impl.Replay(first, count, actions, stride, lengths, out_applied);
+}
+int twixt_step(twixt_batch* b, int64_t env, int32_t action, twixt_step_result* out, int64_t* out_legal) {
+  TW_NEED(b);
+  return b->impl.Step(env, action, out, out_legal);
 }
 int twixt_set_validation(twixt_batch* b, int enabled) {
   TW_NEED(b);

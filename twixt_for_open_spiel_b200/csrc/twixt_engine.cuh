@@ -36,10 +36,10 @@ enum : int { kRed = 0, kBlue = 1 };
 enum : int { kTerminalPlayer = -4 };
 enum : uint32_t { kNoMove = 0xFFFFFFFFu };
 
-// A record is padded to a whole number of 128-byte lines: the kernels that read only its head (header + the two
-// peg planes: legal list / mask, the first loads of apply) then pull whole lines of ONE record out of DRAM
-// instead of lines that straddle two (n = 24: 220 -> 224 words, +1.8 % memory; profiles/, K1 mask).
-TW_HD int record_words(int n) { return (kHeaderWords + kNumStatePlanes * n + 31) & ~31; }
+// (Padding records to whole 128-byte lines -- 224 words at n = 24 -- was measured in round 2: no gain for the
+// kernels that read only a record's head, because their loads already carry the 64-byte L2 fetch hint, which
+// makes any 208-byte head cost four 64-byte granules whatever its offset)
+TW_HD int record_words(int n) { return (kHeaderWords + kNumStatePlanes * n + 3) & ~3; }
 
 TW_HD int tw_popc(uint32_t v) {
 #if defined(__CUDA_ARCH__)

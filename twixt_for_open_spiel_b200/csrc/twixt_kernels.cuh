@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/twixt_b200.h"
+
 namespace twixt {
 
 // device-side counters, one per batch (twixt_stats in the C ABI)
@@ -54,6 +56,7 @@ cudaError_t launch_clone(uint32_t* dst, const uint32_t* src, const int64_t* src_
                          int64_t num_envs, int64_t dst_first, DeviceStats* stats, cudaStream_t s);
 cudaError_t launch_replay(uint32_t* records, int64_t count, int n, const int32_t* actions, int64_t stride,
                           const int32_t* lengths, int32_t* out_applied, DeviceStats* stats, cudaStream_t s);
+cudaError_t launch_step(uint32_t* record, int n, int action, twixt_step_result* out, int64_t* out_legal, cudaStream_t s);
 cudaError_t launch_validate(const uint32_t* records, int64_t count, int n, DeviceStats* stats, cudaStream_t s);
 const char* invalid_reason_text(unsigned code);
 cudaError_t launch_legal_actions(const uint32_t* records, int64_t count, int n, void* out_actions, int elem_bytes,

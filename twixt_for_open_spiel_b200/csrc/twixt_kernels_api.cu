@@ -333,6 +333,61 @@ __global__ void replay_kernel(uint32_t* __restrict__ records, int64_t count, int
   if (out_applied != nullptr) out_applied[i] = k;
 }
 
+// ----------------------------------------------------------------- step ---
+// twixt_step: one env, one warp, one launch -- (reset |) apply, then everything an unbatched caller asks
+// next (twixt.h:38-104): status, CurrentPlayer, IsTerminal, Returns and the ascending LegalActions as int64
+// (open_spiel::Action).  The outputs normally live in the batch's pinned, device-mapped arena.
+__global__ void __launch_bounds__(32) step_kernel(uint32_t* __restrict__ rec, int n, int rw, int action,
+                                                  twixt_step_result* __restrict__ out, int64_t* __restrict__ out_legal) {
+  const int lane = threadIdx.x;
+  RecordRef<1> b{rec, n};
+  int status = 0;
+  if (action == TWIXT_STEP_RESET) {
+    const uint32_t cnt = static_cast<uint32_t>(n * (n - 2));
+    for (int w = lane; w < rw; w += 32) rec[w] = w == 2 ? kNoMove : (w == 3 ? (cnt | (cnt << 16)) : 0u);
+  } else if (action >= 0 && lane == 0) {
+    Header h0;
+    load_header(b, h0);
+    if (!is_legal(b, h0, action)) {
+      status = 1;
+    } else {
+      const int x = action / n;
+      apply_legal_cell<kFloodStack>(b, h0, x, action - x * n);
+      store_header(b, h0);
+    }
+  }
+  __syncwarp();  // lane 0's (or every lane's) record writes are visible to the whole warp
+  Header h;
+  load_header(b, h);
+  const uint32_t w = (lane < n && h.result == kOpen) ? legal_word(b, h, lane) : 0u;
+  const int c = __popc(w);
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  if (out_legal != nullptr) {
+    int64_t* dst = out_legal + (incl - c);
+    uint32_t rest = w;
+    while (rest) {  // ascending: column-major, action = x*n + y (twixtboard.cc:603-605)
+      const int y = tw_ctz(rest);
+      rest &= rest - 1u;
+      *dst++ = static_cast<int64_t>(lane * n + y);
+    }
+  }
+  if (lane == 0) {
+    out->status = status;
+    out->current_player = current_player(h);
+    out->is_terminal = h.result != kOpen ? 1 : 0;
+    out->num_legal = total;
+    const float r = h.result == kRedWin ? 1.0f : (h.result == kBlueWin ? -1.0f : 0.0f);
+    out->returns[0] = r;
+    out->returns[1] = r == 0.0f ? 0.0f : -r;
+  }
+}
+
 // ------------------------------------------------------------- validate ---
 // twixt_import_state takes records from the caller, and the fused playout kernel reads records with its
 // bounds tests deliberately removed (twixt_kernel_playout.cu, PlayoutRef), so what comes in is checked first.
@@ -462,16 +517,18 @@ __global__ void query_kernel(const uint32_t* __restrict__ records, int64_t count
 // AlphaZero-style producer of BASELINE config C5 wants both), so the record is read from HBM once for the
 // two outputs.  The mask is 576 of the 25 920 output bytes at n = 24.
 //
-// TW_OBS_BULK = 1 (an A/B variant): step (C) writes the floats into a double-buffered tile in
-// shared memory and ONE thread hands the whole 25 KB tile to the copy engine (cp.async.bulk shared -> global),
-// so the expansion of env i+1 overlaps the store of env i.
+// TW_OBS_BULK = 1 (the default; 0 keeps the float4-store form for the A/B in DESIGN.md): step (C) writes the
+// floats into a double-buffered tile in shared memory and ONE thread hands the whole tile (25 KB at n = 24) to
+// the copy engine (cp.async.bulk shared -> global, UBLKCP in SASS), so the expansion of env i+1 overlaps the
+// store of env i and no store instruction of the SM touches HBM.  Measured at B = 65 536, n = 24:
+// observation 0.326 -> 0.312 ms, observation + mask 0.339 -> 0.297 ms (0.79 -> 0.89 of the copy peak).
 #ifndef TW_OBS_BULK
-#define TW_OBS_BULK 0
+#define TW_OBS_BULK 1
 #endif
 constexpr int kObsThreads = 256;
 constexpr int kObsPlaneWords = 12 * TWIXT_MAX_BOARD_SIZE;
 constexpr int kObsStreamWords = (12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2) + 31) / 32;
-constexpr int kObsRecordWords = (kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE + 31) & ~31;  // 224 <= 256 threads
+constexpr int kObsRecordWords = (kHeaderWords + kNumStatePlanes * TWIXT_MAX_BOARD_SIZE + 3) & ~3;  // 220 <= 256 threads
 [[maybe_unused]] constexpr int kObsMaxFloats = 12 * TWIXT_MAX_BOARD_SIZE * (TWIXT_MAX_BOARD_SIZE - 2);
 
 // 32 x 32 bit-matrix transpose across a warp: lane i holds row i on entry and column i on return.
@@ -529,16 +586,19 @@ __global__ void __launch_bounds__(kObsThreads, TW_OBS_BULK ? 4 : 8) observation_
       const uint32_t colw = lane < n ? obs_plane_word(b, warp, lane) : 0u;
       const uint32_t roww = warp_transpose32(colw, lane);
       if (lane < n) rowbits[warp * n + (n - 1 - lane)] = (roww >> 1) & wmask;  // (r, c) <- cell (c+1, n-1-r)
-    } else {
-      // blue planes: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column word, reversed
-      for (int t = tid - 6 * 32; t < 6 * n; t += 2 * 32) {
+    }
+    {
+      // blue planes: (r, c) <- cell (n-1-r, n-2-c): rows 1..n-2 of one column word, reversed.  One word per
+      // thread, taken from the top of the block so that the warps busy with a transpose get the fewest.
+      const int t = kObsThreads - 1 - tid;
+      if (t < 6 * n) {
         const int p = t / n, x = t - p * n;
         rowbits[(6 + p) * n + (n - 1 - x)] = (__brev(obs_plane_word(b, 6 + p, x)) >> (32 - (n - 1))) & wmask;
       }
-      if (kMask && tid >= kObsThreads - 32 && lane < n) {  // TwixTState::LegalActions (twixt.h:86-90) as a bit word per column
+      if (kMask && tid < n) {  // TwixTState::LegalActions (twixt.h:86-90) as a bit word per column
         Header h;
         unpack_header(rec[0], rec[1], rec[2], rec[3], h);
-        legalw[lane] = h.result != kOpen ? 0u : legal_word(b, h, lane);
+        legalw[tid] = h.result != kOpen ? 0u : legal_word(b, h, tid);
       }
     }
     __syncthreads();
@@ -713,6 +773,11 @@ cudaError_t launch_replay(uint32_t* records, int64_t count, int n, const int32_t
   const int64_t blocks = (count + threads - 1) / threads;
   replay_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(records, count, n, record_words(n), actions, stride,
                                                                   lengths, out_applied, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step(uint32_t* record, int n, int action, twixt_step_result* out, int64_t* out_legal, cudaStream_t s) {
+  step_kernel<<<1, 32, 0, s>>>(record, n, record_words(n), action, out, out_legal);
   return cudaGetLastError();
 }
 

@@ -90,8 +90,7 @@ class TwixTGame:
 
     def new_initial_state(self) -> "TwixTState":
         pool, idx = self._take_slot()
-        pool.reset(idx, 1)
-        return TwixTState(self, pool, idx)
+        return TwixTState(self, pool, idx, step=STEP_RESET)
 
     def num_distinct_actions(self) -> int:
         return self._info.num_distinct_actions
@@ -140,13 +139,14 @@ class TwixTGame:
         if history:
             state._pool.replay(np.asarray([history], dtype=np.int32), state._idx)
             state._history = history
+            state._step(STEP_QUERY)
         return state
 
     def new_state_from_record(self, record) -> "TwixTState":
         """A state from an exported packed record (twixt_import_state); its history is unknown."""
         pool, idx = self._take_slot()
         pool.import_state(np.ascontiguousarray(record, dtype=np.uint32), idx)
-        return TwixTState(self, pool, idx, history=None)
+        return TwixTState(self, pool, idx, history=None, step=STEP_QUERY)
 
     # -- slot pool -------------------------------------------------------------
     def _take_slot(self):
@@ -160,12 +160,27 @@ class TwixTGame:
         self._free.append((pool, idx))
 
 
+STEP_QUERY, STEP_RESET = -1, -2  # include/twixt_b200.h
+
+
 class TwixTState:
-    def __init__(self, game: TwixTGame, pool: TwixTBatch, idx: int, history: Optional[List[int]] = None):
+    """Like the C++ adapter (adapter/twixt_b200_game.h) a state keeps the answer of its last twixt_step --
+    player, terminal flag, returns, legal actions -- so apply_action is one kernel launch and the four query
+    methods touch no GPU."""
+
+    def __init__(self, game: TwixTGame, pool: TwixTBatch, idx: int, history: Optional[List[int]] = None,
+                 step: Optional[int] = None, now=None):
         self._game = game
         self._pool = pool
         self._idx = idx
         self._history: List[int] = list(history or [])
+        self._now = now
+        if step is not None:
+            self._step(step)
+
+    def _step(self, action: int) -> None:
+        _, player, terminal, returns, legal = self._pool.step(self._idx, action)
+        self._now = (player, terminal, returns, [int(a) for a in legal])
 
     def __del__(self):
         try:
@@ -175,13 +190,13 @@ class TwixTState:
 
     # -- State surface (twixt.h:31-112) -----------------------------------------
     def current_player(self) -> int:
-        return int(self._pool.current_player(self._idx, 1)[0])
+        return self._now[0]
 
     def is_terminal(self) -> bool:
-        return bool(self._pool.is_terminal(self._idx, 1)[0])
+        return self._now[1]
 
     def returns(self) -> List[float]:
-        return [float(v) for v in self._pool.returns(self._idx, 1)[0]]
+        return list(self._now[2])
 
     def rewards(self) -> List[float]:
         return self.returns()
@@ -190,8 +205,7 @@ class TwixTState:
         return self.returns()[player]
 
     def legal_actions(self, player: Optional[int] = None) -> List[int]:
-        acts, cnt = self._pool.legal_actions(self._idx, 1)
-        return [int(a) for a in acts[0, :int(cnt[0])]]
+        return list(self._now[3])
 
     def legal_actions_mask(self, player: Optional[int] = None) -> List[int]:
         return [int(v) for v in self._pool.legal_mask(self._idx, 1)[0]]
@@ -200,7 +214,7 @@ class TwixTState:
         a = int(action)
         if a < 0 or a > 0x7FFFFFFF:
             raise SpielFatalError("Not a legal action: %d" % a)
-        self._pool.apply(np.array([a], dtype=np.int32), self._idx)  # raises "Not a legal action: N"
+        self._step(a)  # raises "Not a legal action: N" and leaves the state as it was
         self._history.append(a)
 
     def clone(self) -> "TwixTState":
@@ -209,7 +223,7 @@ class TwixTState:
             pool.clone(self._idx, idx, 1)
         else:
             pool.clone_from(idx, self._pool, self._idx, 1)
-        return TwixTState(self._game, pool, idx, self._history)
+        return TwixTState(self._game, pool, idx, self._history, now=self._now)
 
     def observation_tensor(self, player: int = 0) -> List[float]:
         if player < 0 or player >= 2:  # SPIEL_CHECK_GE / _LT, twixt.cc:103-104
