@@ -92,8 +92,12 @@ def run(n, envs, reps):
     for rnd in range(2):  # two rounds, so that a drifting clock shows up as a difference between rounds
         for name in names:
             env = dict(os.environ, TWIXT_B200_LIB=os.path.join(VDIR, name))
-            res = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(n), str(envs), str(reps)],
-                                 capture_output=True, text=True, env=env)
+            try:
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(n), str(envs), str(reps)],
+                                     capture_output=True, text=True, env=env, timeout=150)
+            except subprocess.TimeoutExpired:
+                print("%-28s round %d  TIMEOUT (hung kernel?)" % (name, rnd), flush=True)
+                return
             line = [l for l in res.stdout.splitlines() if l.startswith("RESULT")]
             print("%-28s round %d  %s" % (name, rnd, line[0] if line else "FAILED: " + res.stderr[-400:]), flush=True)
 

@@ -46,6 +46,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "twixt_b200.h"
 #include "twixt_engine.cuh"
 #include "twixt_kernels.cuh"
@@ -507,31 +510,44 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
   }
 }
 
+// (A PAIRED form of this kernel -- two warps per 32 envs, a selector owning header / pegs / selection and an
+// evaluator owning links / flags / floods, talking through mailbox words and named barriers -- was built and
+// measured in round 2: bit-exact, but 29.2 ms instead of 18.2 ms per launch.  The single warp already runs
+// the two chains as instruction-level parallelism; splitting them across warps halved each warp's issue rate
+// and added the waits.  profiles/r2_playout_paired_experiment.txt)
+
 int g_num_sms = 0;
+
+#define TW_PLAYOUT_KERNEL playout_kernel
+constexpr int kLaunchThreads = kPlayoutThreads, kEnvsPerBlock = kPlayoutThreads;
+__host__ constexpr size_t launch_smem(int n) { return static_cast<size_t>(kEnvsPerBlock) * playout_words(n) * sizeof(uint32_t); }
 
 template <int NT, bool kTrace>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(a.n) * sizeof(uint32_t);
+  const size_t smem = launch_smem(a.n);
   // persistent grid: as many blocks as fit on the device at once (or fewer for small ranges)
   int per_sm = 0;
   cudaError_t e =
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, playout_kernel<NT, kTrace>, kPlayoutThreads, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, TW_PLAYOUT_KERNEL<NT, kTrace>, kLaunchThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  int64_t blocks = (a.count + kPlayoutThreads - 1) / kPlayoutThreads;
+  int64_t blocks = (a.count + kEnvsPerBlock - 1) / kEnvsPerBlock;
   const int64_t resident = static_cast<int64_t>(g_num_sms > 0 ? g_num_sms : 148) * per_sm;
   if (blocks > resident) blocks = resident;
-  playout_kernel<NT, kTrace><<<static_cast<unsigned>(blocks), kPlayoutThreads, smem, s>>>(a);
+  if (getenv("TWIXT_B200_DEBUG") != nullptr)
+    fprintf(stderr, "[twixt_b200] playout n=%d: %lld blocks x %d threads, %zu B smem, %d blocks/SM resident\n", a.n,
+            static_cast<long long>(blocks), kLaunchThreads, smem, per_sm);
+  TW_PLAYOUT_KERNEL<NT, kTrace><<<static_cast<unsigned>(blocks), kLaunchThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
 template <int NT, bool kTrace>
 cudaError_t setup_one(int n_for_size) {
-  const size_t smem = static_cast<size_t>(kPlayoutThreads) * playout_words(n_for_size) * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(playout_kernel<NT, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = launch_smem(n_for_size);
+  cudaError_t e = cudaFuncSetAttribute(TW_PLAYOUT_KERNEL<NT, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(playout_kernel<NT, kTrace>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(TW_PLAYOUT_KERNEL<NT, kTrace>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 
