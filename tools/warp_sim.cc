@@ -9,6 +9,8 @@
 //             move only reads its own pegs' flags, so the opponent moves while c's flood is still running
 //   policy 2  policy 1 + the FLOOD region runs twice in iterations where at least T lanes owe visits
 //   policy 3  policy 1 + MOVE is skipped in iterations where fewer than T lanes are ready to move
+//   policy 4  policy 1 + the FLOOD region only runs every T-th iteration (visits are batched)
+//   policy 5  policy 1 + the FLOOD region only runs when at least T lanes owe a visit, or one has waited 3 iterations
 // Build: g++ -O2 -std=c++17 -I twixt_for_open_spiel_b200/csrc -o /tmp/warp_sim tools/warp_sim.cc
 #include <cstdint>
 #include <cstdio>
@@ -181,6 +183,15 @@ int main(int argc, char** argv) {
       }
       // FLOOD (possibly twice)
       int passes = 1;
+      if (policy == 4 && (iters % thresh) != 0) passes = 0;
+      if (policy == 5) {
+        int owing = 0;
+        static long waited = 0;
+        for (int l = 0; l < 32; ++l) owing += L[l].have && (!L[l].stk.empty() || L[l].pendc[0] || L[l].pendc[1]);
+        if (owing == 0) waited = 0;
+        else if (owing < thresh && waited < 2) { passes = 0; ++waited; }
+        else waited = 0;
+      }
       if (policy == 2) {
         int owing = 0;
         for (int l = 0; l < 32; ++l) owing += L[l].have && (!L[l].stk.empty() || L[l].pendc[0] || L[l].pendc[1]);
