@@ -398,8 +398,8 @@ class TwixTBatch {
              int32_t* out_applied) {
     TW_TRY(CheckRange(first, count));
     if (stride < 0) return fail(TWIXT_EINVAL, "stride must be >= 0");
-    if (count == 0 || stride == 0) return TWIXT_OK;
-    if (actions == nullptr) return fail(TWIXT_EINVAL, "null actions pointer");
+    if (count == 0) return TWIXT_OK;
+    if (actions == nullptr && stride > 0) return fail(TWIXT_EINVAL, "null actions pointer");
     DeviceGuard g(device_);
     ScratchReset();
     Staged in, len, ap;
