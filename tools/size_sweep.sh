@@ -1,5 +1,5 @@
 #!/bin/bash
-# playout throughput per board size (compile-time-size instantiations: 8, 12, 24; the others run the run-time-size kernel)
-for n in 5 8 10 12 16 20 23 24; do
-  python bench.py --board-size $n --steps 5 --warmup 3 --no-cpu --no-kernels 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('n=$n', '%.4e steps/s' % d['value'], '%.3f ms' % d['roofline']['kernel_ms'], 'mean plies/game %.1f' % (d['outcomes']['plies']/max(d['outcomes']['games'],1)))"
+# playout throughput per board size with the product library (every size has its own compile-time-size kernel)
+for n in ${@:-5 8 10 12 14 15 16 17 18 19 20 21 22 23 24}; do
+  echo -n "n=$n  "; python tools/ab_playout.py child $n 1048576 3 2>&1 | tail -1
 done

@@ -64,7 +64,7 @@ namespace {
 #ifndef TW_PLAYOUT_MIN_BLOCKS
 #define TW_PLAYOUT_MIN_BLOCKS 1
 #endif
-constexpr int kPlayoutThreads = TW_PLAYOUT_THREADS;  // 4 warps per block
+constexpr int kPlayoutThreads = TW_PLAYOUT_THREADS;  // 4 warps per block (the default; see playout_threads)
 constexpr int kSmemPlanes = 8;        // P_RED .. P_END
 #ifndef TW_PLAYOUT_STACK_WORDS
 #define TW_PLAYOUT_STACK_WORDS 24
@@ -73,7 +73,11 @@ constexpr int kStackWords = TW_PLAYOUT_STACK_WORDS;  // flood stack entries (one
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
-__host__ __device__ constexpr int playout_words(int n) { return kSmemPlanes * n + kStackWords + kCacheWords; }
+// words of shared memory per env: the planes and the flood stack; the run-time-size form (never instantiated,
+// see PlayoutRef) would keep its count cache there too
+__host__ __device__ constexpr int playout_words(int n, bool cache_in_smem = false) {
+  return kSmemPlanes * n + kStackWords + (cache_in_smem ? kCacheWords : 0);
+}
 
 // -DTW_PLAYOUT_BOUNDS_CHECK=1 builds the INSTRUMENTED variant used by tests/ (never the product build): every
 // shared-memory access of the rules and of the flood stack is tested against the lane's own column,
@@ -97,7 +101,7 @@ struct PlayoutRef {
 #if TW_PLAYOUT_BOUNDS_CHECK
   unsigned long long* viol;
   __device__ __forceinline__ int chk(int word) const {
-    if (word < 0 || word >= playout_words(n())) {
+    if (word < 0 || word >= playout_words(n(), NT == 0)) {
       atomicAdd(viol, 1ull);
       return 0;
     }
@@ -240,21 +244,38 @@ struct SmemStack {
 static_assert(kStackWords >= 4, "a flood visit pushes up to four entries");
 
 // resident blocks per SM the register allocation should allow: what shared memory allows for that size
+// Block geometry per board size.  The resident warps per SM are what this latency-bound kernel lives on
+// (profiles/r2_playout_occupancy_scaling.txt), and they are capped by shared memory: blocks of 128 threads
+// (with 1 KB reserved per block) leave room unused at the sizes where two of them fit but three do not.  For
+// those sizes ONE block of 9 or 10 warps is used instead (10 is what 195 registers per thread allow):
+// measured at n = 16, 28.8 -> 30.6 G steps/s.  n >= 22 fits 8 warps either way, n <= 14 fits three or four
+// blocks of 128 threads.
+__host__ __device__ constexpr int playout_blocks_of_128(int nt) { return (227 * 1024) / (128 * playout_words(nt) * 4 + 1024); }
+__host__ __device__ constexpr int playout_one_block_warps(int nt) {
+  return ((227 * 1024 - 1024) / (playout_words(nt) * 4)) / 32 > 10 ? 10 : ((227 * 1024 - 1024) / (playout_words(nt) * 4)) / 32;
+}
+__host__ __device__ constexpr int playout_threads(int nt) {
+  return (TW_PLAYOUT_THREADS != 128 || nt == 0)           ? TW_PLAYOUT_THREADS  // (experiments: a forced block size)
+         : (playout_blocks_of_128(nt) == 2 && playout_one_block_warps(nt) > 8) ? 32 * playout_one_block_warps(nt)
+                                                                                : 128;
+}
 __host__ __device__ constexpr int playout_min_blocks(int nt) {
-  return nt == 0 ? TW_PLAYOUT_MIN_BLOCKS : (227 * 1024) / (kPlayoutThreads * playout_words(nt) * 4 + 1024) > 4
-                                               ? 4
-                                               : (227 * 1024) / (kPlayoutThreads * playout_words(nt) * 4 + 1024);
+  return nt == 0 ? TW_PLAYOUT_MIN_BLOCKS
+                 : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + 1024) > 4
+                       ? 4
+                       : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + 1024);
 }
 
 // kTrace: write the action trace (only parity tests ask for it; the branch is compiled out otherwise)
 template <int NT, bool kTrace>
-__global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playout_kernel(const PlayoutArgs a) {
+__global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) playout_kernel(const PlayoutArgs a) {
+  constexpr int kThreads = playout_threads(NT);
   extern __shared__ uint4 smem_raw[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
   const int n = NT > 0 ? NT : a.n;
   const int rw = record_words(n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* mine = smem + warp * (playout_words(n) * 32) + lane;
+  uint32_t* mine = smem + warp * (playout_words(n, NT == 0) * 32) + lane;
   const int plane_quads = (kSmemPlanes * n) / 4;  // 8n staged words = 2n 16-byte pieces (planes start 16-byte aligned)
   const uint32_t k_lo = static_cast<uint32_t>(a.seed), k_hi = static_cast<uint32_t>(a.seed >> 32);
 
@@ -391,10 +412,10 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
 
   // every thread only ever touches its own column of the staging buffer: no barrier needed anywhere.
   // Tickets: the first gridDim.x*blockDim.x envs are pre-assigned, the rest are handed out by a counter.
-  const int64_t preassigned = static_cast<int64_t>(gridDim.x) * kPlayoutThreads;
+  const int64_t preassigned = static_cast<int64_t>(gridDim.x) * kThreads;
   bool exhausted = false;
   {
-    const int64_t e = blockIdx.x * static_cast<int64_t>(kPlayoutThreads) + threadIdx.x;
+    const int64_t e = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
     if (e < a.count) begin_take(e);
     else exhausted = true;
   }
@@ -519,12 +540,12 @@ __global__ void __launch_bounds__(kPlayoutThreads, playout_min_blocks(NT)) playo
 int g_num_sms = 0;
 
 #define TW_PLAYOUT_KERNEL playout_kernel
-constexpr int kLaunchThreads = kPlayoutThreads, kEnvsPerBlock = kPlayoutThreads;
-__host__ constexpr size_t launch_smem(int n) { return static_cast<size_t>(kEnvsPerBlock) * playout_words(n) * sizeof(uint32_t); }
+__host__ constexpr size_t launch_smem(int n) { return static_cast<size_t>(playout_threads(n)) * playout_words(n) * sizeof(uint32_t); }
 
 template <int NT, bool kTrace>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
-  const size_t smem = launch_smem(a.n);
+  constexpr int kLaunchThreads = playout_threads(NT), kEnvsPerBlock = playout_threads(NT);
+  const size_t smem = launch_smem(NT);
   // persistent grid: as many blocks as fit on the device at once (or fewer for small ranges)
   int per_sm = 0;
   cudaError_t e =
