@@ -116,3 +116,54 @@ def test_observation_index_arithmetic_is_exact():
         m = ((1 << 20) + w - 1) // w
         for j in range(0, 12 * 24 * 22 + 64):
             assert (j * m) >> 20 == j // w and j * m < 2 ** 32
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """_lib.py's ctypes mirrors of the ABI structs have the size and field offsets the C compiler gives them."""
+    import subprocess
+    from twixt_for_open_spiel_b200 import _lib
+    src = tmp_path / "layout.c"
+    fields = {"twixt_game_info": [f for f, _ in _lib.GameInfo._fields_],
+              "twixt_stats": [f for f, _ in _lib.Stats._fields_],
+              "twixt_step_result": [f for f, _ in _lib.StepResult._fields_]}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "twixt_b200.h"', 'int main(void) {']
+    for name, fs in fields.items():
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (name, name))
+        for f in fs:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (name, f))
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().splitlines()
+    mirrors = {"twixt_game_info": _lib.GameInfo, "twixt_stats": _lib.Stats, "twixt_step_result": _lib.StepResult}
+    assert len(out) == 3
+    for line in out:
+        toks = line.split()
+        cls = mirrors[toks[0]]
+        assert C.sizeof(cls) == int(toks[1]), toks[0]
+        assert [getattr(cls, f).offset for f, _ in cls._fields_] == [int(t) for t in toks[2:]], toks[0]
+
+
+def test_shard_helpers_need_no_gpu():
+    """twixt_shard_range / twixt_stats_accumulate (what sharding.py itself calls): shares are contiguous,
+    cover the range and differ by at most one env."""
+    from twixt_for_open_spiel_b200 import _lib
+    from twixt_for_open_spiel_b200.sharding import shard_range
+    for total, world in ((1 << 20, 8), (10, 4), (7, 7), (3, 5), (0, 2)):
+        nxt, sizes = 0, []
+        for r in range(world):
+            first, count = shard_range(total, world, r)
+            assert first == nxt
+            nxt += count
+            sizes.append(count)
+        assert nxt == total and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 4, 4)
+    lib = _lib.load()
+    acc, part = _lib.Stats(), _lib.Stats()
+    part.plies, part.games, part.max_length, part.kernel_launches = 11, 2, 9, 1
+    for _ in range(3):
+        assert lib.twixt_stats_accumulate(C.byref(acc), C.byref(part)) == 0
+    assert (acc.plies, acc.games, acc.max_length, acc.kernel_launches) == (33, 6, 9, 3)
