@@ -9,5 +9,5 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_th
 python tools/kernel_probe.py > gpurun_out/r2_probe_plain.log 2>&1 && ncu --metrics $M --clock-control none -k regex:"legal|observation|apply|validate|replay|clone|reset|step" --csv --log-file gpurun_out/r2_api_kernels.csv python tools/kernel_probe.py > gpurun_out/r2_probe_ncu.log 2>&1
 python bench.py --steps 2 --warmup 3 --no-cpu --no-kernels --no-configs > gpurun_out/r2_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:playout_kernel -s 3 -c 1 -o gpurun_out/r2_playout_final python bench.py --steps 2 --warmup 3 --no-cpu --no-kernels --no-configs > gpurun_out/r2_ncu_playout.log 2>&1
 python bench.py --steps 2 --warmup 3 --no-cpu --no-kernels --no-configs > gpurun_out/r2_plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-kernels --no-configs > gpurun_out/r2_ncu_launches.log 2>&1
-python tools/kernel_probe.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:observation_kernel -s 8 -c 1 -o gpurun_out/r2_observation python tools/kernel_probe.py > gpurun_out/r2_ncu_obs.log 2>&1
+python tools/kernel_probe.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:observation_kernel -s 2 -c 1 -o gpurun_out/r2_observation python tools/kernel_probe.py > gpurun_out/r2_ncu_obs.log 2>&1
 tail -3 gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_smoke.log | tail -2; tail -c 400 gpurun_out/r2_bench.err
