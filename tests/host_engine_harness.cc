@@ -35,7 +35,20 @@ struct CachedRec : public RecordRef<1> {
 // An accessor with the fused kernel's shared-memory layout (twixt_kernel_playout.cu, PlayoutRef): planes in
 // the order BLUE, RED, links, START, END followed by the flood-stack words, and link-window / flag reads
 // WITHOUT bounds tests.  The stack words are poisoned so that a read off the board that mattered would show.
+// select_bit_lut's table, as the kernel builds it in shared memory
+static const uint8_t* host_select_lut() {
+  static uint8_t lut[8 * 256];
+  static bool ready = false;
+  if (!ready) {
+    for (int e = 0; e < 8 * 256; ++e) fill_select_lut(lut, e);
+    ready = true;
+  }
+  return lut;
+}
+
 struct SmemRec {
+  static constexpr bool kSelectLut = true;
+  const uint8_t* select_lut() const { return host_select_lut(); }
   std::vector<uint32_t> w;
   uint32_t* blocked;  // the record's blocked plane (global memory in the kernel)
   int n_rt;

@@ -71,6 +71,7 @@ constexpr int kSmemPlanes = 8;        // P_RED .. P_END
 #endif
 constexpr int kStackWords = TW_PLAYOUT_STACK_WORDS;  // flood stack entries (one per word; tests build with 4)
 constexpr int kCacheWords = 6;        // per-column count cache, four columns per word
+constexpr int kSelectLutBytes = 8 * 256;  // select_bit_lut: [rank 0..7][byte]
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 // words of shared memory per env: the planes and the flood stack; the run-time-size form (never instantiated,
@@ -166,6 +167,9 @@ struct PlayoutRef {
   // store->load round trip after a move); the run-time-size instantiation keeps them in shared memory
   // after the planes and the stack.
   static constexpr bool kCountCache = true;
+  static constexpr bool kSelectLut = true;
+  const uint8_t* lut;  // shared memory: select_bit_lut's table, filled once per block
+  __device__ __forceinline__ const uint8_t* select_lut() const { return lut; }
   static constexpr bool kCacheInRegs = NT > 0;
   uint32_t cw[kCacheWords];
   __device__ __forceinline__ uint32_t* cache_word(int i) const { return p + (kSmemPlanes * n() + kStackWords + i) * 32; }
@@ -250,9 +254,10 @@ static_assert(kStackWords >= 4, "a flood visit pushes up to four entries");
 // those sizes ONE block of 9 or 10 warps is used instead (10 is what 195 registers per thread allow):
 // measured at n = 16, 28.8 -> 30.6 G steps/s.  n >= 22 fits 8 warps either way, n <= 14 fits three or four
 // blocks of 128 threads.
-__host__ __device__ constexpr int playout_blocks_of_128(int nt) { return (227 * 1024) / (128 * playout_words(nt) * 4 + 1024); }
+constexpr int kBlockOverhead = 1024 + 8 * 256;  // reserved by CUDA + the select table
+__host__ __device__ constexpr int playout_blocks_of_128(int nt) { return (227 * 1024) / (128 * playout_words(nt) * 4 + kBlockOverhead); }
 __host__ __device__ constexpr int playout_one_block_warps(int nt) {
-  return ((227 * 1024 - 1024) / (playout_words(nt) * 4)) / 32 > 10 ? 10 : ((227 * 1024 - 1024) / (playout_words(nt) * 4)) / 32;
+  return ((227 * 1024 - kBlockOverhead) / (playout_words(nt) * 4)) / 32 > 10 ? 10 : ((227 * 1024 - kBlockOverhead) / (playout_words(nt) * 4)) / 32;
 }
 __host__ __device__ constexpr int playout_threads(int nt) {
   return (TW_PLAYOUT_THREADS != 128 || nt == 0)           ? TW_PLAYOUT_THREADS  // (experiments: a forced block size)
@@ -261,9 +266,9 @@ __host__ __device__ constexpr int playout_threads(int nt) {
 }
 __host__ __device__ constexpr int playout_min_blocks(int nt) {
   return nt == 0 ? TW_PLAYOUT_MIN_BLOCKS
-                 : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + 1024) > 4
+                 : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + kBlockOverhead) > 4
                        ? 4
-                       : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + 1024);
+                       : (227 * 1024) / (playout_threads(nt) * playout_words(nt) * 4 + kBlockOverhead);
 }
 
 // kTrace: write the action trace (only parity tests ask for it; the branch is compiled out otherwise)
@@ -288,6 +293,13 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
   b.p = mine;
   b.gblk = nullptr;
   b.n_rt = n;
+  {
+    // the 2 KB look-up table of select_bit_lut behind the env columns (the only block-wide step of the kernel)
+    uint8_t* lut = reinterpret_cast<uint8_t*>(smem + kThreads * playout_words(n, NT == 0));
+    for (int e = threadIdx.x; e < kSelectLutBytes; e += kThreads) fill_select_lut(lut, e);
+    __syncthreads();
+    b.lut = lut;
+  }
 #pragma unroll
   for (int i = 0; i < kCacheWords; ++i) b.cw[i] = 0u;
   SmemStack stk;
@@ -540,7 +552,9 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
 int g_num_sms = 0;
 
 #define TW_PLAYOUT_KERNEL playout_kernel
-__host__ constexpr size_t launch_smem(int n) { return static_cast<size_t>(playout_threads(n)) * playout_words(n) * sizeof(uint32_t); }
+__host__ constexpr size_t launch_smem(int n) {
+  return static_cast<size_t>(playout_threads(n)) * playout_words(n) * sizeof(uint32_t) + kSelectLutBytes;
+}
 
 template <int NT, bool kTrace>
 cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
@@ -565,7 +579,7 @@ cudaError_t launch_nt(const PlayoutArgs& a, cudaStream_t s) {
 template <int NT, bool kTrace>
 cudaError_t setup_one(int n_for_size) {
   const size_t smem = launch_smem(n_for_size);
-  if (smem > 227 * 1024) return cudaSuccess;  // (an experimental block geometry that does not fit this size: the launch will say so)
+  if (smem + 1024 > 227 * 1024) return cudaSuccess;  // (an experimental block geometry that does not fit this size: the launch will say so)
   cudaError_t e = cudaFuncSetAttribute(TW_PLAYOUT_KERNEL<NT, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
