@@ -154,13 +154,12 @@ int playout_like_kernel(B& b, Header& h, int n, uint64_t seed, uint64_t stream, 
     }
     if (!stk.empty() || pend != 0u) {
       const bool begin = stk.empty();
-      const uint32_t next_mover = h.ply & 1u;
-      const uint32_t col = ((pend >> (2u * next_mover)) & 3u) != 0u ? next_mover : (next_mover ^ 1u);
-      const bool start = ((pend >> (2u * col)) & kFloodStart) != 0u;
-      fplane = begin ? (start ? P_START : P_END) : fplane;
-      fcol = begin ? col : fcol;
-      pend &= begin ? ~((start ? kFloodStart : kFloodEnd) << (2u * col)) : ~0u;
-      const uint32_t e = stk.top_or(col == kRed ? origin_r : origin_b);
+      const uint32_t lsb = pend & (0u - pend);  // the lowest owed flood first, as in the kernel
+      const bool blue = (lsb & 12u) != 0u;
+      fplane = begin ? ((lsb & 5u) != 0u ? P_START : P_END) : fplane;
+      fcol = begin ? (blue ? 1u : 0u) : fcol;
+      pend ^= begin ? lsb : 0u;
+      const uint32_t e = stk.top_or(blue ? origin_b : origin_r);
       flood_visit_entry(b, fplane, stk, e);
       if (stk.empty() && stk.overflow) {
         flood_closure(b, fcol == kRed ? P_RED : P_BLUE, fplane);

@@ -745,7 +745,7 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
   // (gt == 0 only when there is no legal cell at all -- a speculative selection whose result is never
   // used; the clamps keep its loads inside the board)
   const int j = gt ? (tw_ctz(gt) >> 3) : 0;
-  const int before = j == 0 ? 0 : static_cast<int>((sp >> (8 * (j - 1))) & 0xFFu);
+  const int before = static_cast<int>(((sp << 8) >> (8 * j)) & 0xFFu);  // inclusive prefix of byte j-1 (0 for j = 0)
   const int x = (4 * si + j) < n ? (4 * si + j) : (n - 1);
   out_x = x;
   if constexpr (B::kSelectLut) {

@@ -502,14 +502,15 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
     // others visit the entry on top of their stack.
     if (!stk.empty() || pend != 0u) {
       const bool begin = stk.empty();
-      // the next flood to start: the one the sooner move waits for, i.e. of the colour that moves next
-      const uint32_t next_mover = h.ply & 1u;
-      const uint32_t col = ((pend >> (2u * next_mover)) & 3u) != 0u ? next_mover : (next_mover ^ 1u);
-      const bool start = ((pend >> (2u * col)) & kFloodStart) != 0u;
-      fplane = begin ? (start ? P_START : P_END) : fplane;
-      fcol = begin ? col : fcol;
-      pend &= begin ? ~((start ? kFloodStart : kFloodEnd) << (2u * col)) : ~0u;
-      const uint32_t e = stk.top_or(col == kRed ? origin_r : origin_b);
+      // the next flood to start: the lowest owed one (red START, red END, blue START, blue END) -- any order
+      // gives the same planes, and this one is three instructions (the "colour that moves next first" rule it
+      // replaces cost a dozen with its variable shifts, for 0.1 % fewer iterations in tools/warp_sim.cc)
+      const uint32_t lsb = pend & (0u - pend);
+      const bool blue = (lsb & 12u) != 0u;
+      fplane = begin ? ((lsb & 5u) != 0u ? P_START : P_END) : fplane;
+      fcol = begin ? (blue ? 1u : 0u) : fcol;
+      pend ^= begin ? lsb : 0u;
+      const uint32_t e = stk.top_or(blue ? origin_b : origin_r);
       flood_visit_entry(b, fplane, stk, e);
       if (stk.empty() && stk.overflow) {
         flood_closure(b, fcol == kRed ? P_RED : P_BLUE, fplane);
