@@ -740,12 +740,16 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
       k -= static_cast<int>(p4 >> 24);
     }
   }
-  // first byte whose inclusive prefix exceeds sk
-  const uint32_t gt = bytes_gt(sp, bytes4(static_cast<uint32_t>(sk)));
-  // (gt == 0 only when there is no legal cell at all -- a speculative selection whose result is never
-  // used; the clamps keep its loads inside the board)
-  const int j = gt ? (tw_ctz(gt) >> 3) : 0;
-  const int before = static_cast<int>(((sp << 8) >> (8 * j)) & 0xFFu);  // inclusive prefix of byte j-1 (0 for j = 0)
+  // first byte whose inclusive prefix exceeds sk.  The bytes of sp are prefix sums, i.e. non-decreasing, so that
+  // byte's index is the NUMBER of bytes not above sk: three independent compares (the fourth byte is above sk for
+  // every valid k) instead of a bytewise compare emulated in six dependent instructions plus a find-first-set --
+  // this is the tail of the playout kernel's loop-carried selection chain.  `before` = the prefix of the byte
+  // in front of it.  (With no legal cell at all -- a speculative selection that is never used -- j = 3 and the
+  // clamp below keeps the loads on the board.)
+  const int p0 = static_cast<int>(sp & 0xFFu), p1 = static_cast<int>((sp >> 8) & 0xFFu), p2 = static_cast<int>((sp >> 16) & 0xFFu);
+  const bool le0 = p0 <= sk, le1 = p1 <= sk, le2 = p2 <= sk;
+  const int j = (le0 ? 1 : 0) + (le1 ? 1 : 0) + (le2 ? 1 : 0);
+  const int before = le2 ? p2 : (le1 ? p1 : (le0 ? p0 : 0));
   const int x = (4 * si + j) < n ? (4 * si + j) : (n - 1);
   out_x = x;
   if constexpr (B::kSelectLut) {
