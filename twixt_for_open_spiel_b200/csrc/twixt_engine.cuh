@@ -443,8 +443,10 @@ TW_HD void swap_first_move(B& b, Header& h, int& x, int& y) {
 
 // kSwapDone: the caller has already run swap_first_move for a swapping action (the fused playout kernel
 // does it in its rare-events block, so that the per-move code has no branch for it).
-template <bool kSwapDone = false, class B>
-TW_HD Placement begin_move(B& b, Header& h, int x, int y) {
+// kPreloaded: `own_word` is the mover's peg word of column x as it stands (the fused playout kernel has it in a
+// register from choosing the cell, which saves a shared-memory round trip at the head of the move).
+template <bool kSwapDone = false, bool kPreloaded = false, class B>
+TW_HD Placement begin_move(B& b, Header& h, int x, int y, uint32_t own_word = 0u) {
   const int n = b.n();
   Placement p;
   p.player = static_cast<int>(h.ply & 1u);
@@ -453,7 +455,7 @@ TW_HD Placement begin_move(B& b, Header& h, int x, int y) {
   p.x = x;
   p.y = y;
   const int own = p.player == kRed ? P_RED : P_BLUE;
-  b.st_pegs(own, x, b.ld_pegs(own, x) | (1u << y));
+  b.st_pegs(own, x, (kPreloaded ? own_word : b.ld_pegs(own, x)) | (1u << y));
   b.note_peg(x, y, +1);
   h.cnt[kRed] -= (x >= 1 && x <= n - 2) ? 1 : 0;
   h.cnt[kBlue] -= (y >= 1 && y <= n - 2) ? 1 : 0;
@@ -717,7 +719,7 @@ TW_HD uint32_t count_cache_legal4(uint32_t w, const CountMode& m, int n, int i) 
 }
 
 template <class B>
-TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, int& out_y) {
+TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, int& out_y, uint32_t* out_pegs = nullptr) {
   const int n = b.n();
   constexpr int kMaxWords = 6;  // ceil(24 / 4)
   const int words = (n + 3) / 4;
@@ -755,7 +757,13 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
   if constexpr (B::kSelectLut) {
     // (a speculative selection with no legal cell left may land on an edge column: the masks below keep the
     // look-up inside the table, and its result is never used)
-    const uint32_t w = legal_word_selected(b, h, x) & 0xFFFFFFu;
+    const uint32_t red = b.ld_pegs(P_RED, x), blue = b.ld_pegs(P_BLUE, x);
+    if (out_pegs != nullptr) {  // the chosen column's peg words, for begin_move<.., kPreloaded>
+      out_pegs[0] = red;
+      out_pegs[1] = blue;
+    }
+    const uint32_t play = (h.ply & 1u) == kRed ? full_rows(n) : inner_rows(n);  // (legal_word_selected, spelled out)
+    const uint32_t w = (h.ply == 1u ? play : (play & ~(red | blue))) & 0xFFFFFFu;
     out_y = select_bit_lut(b.select_lut(), w, sk - before);
   } else {
     out_y = select_bit(legal_word(b, h, x), sk - before);
@@ -766,9 +774,9 @@ TW_HD void select_legal_cached(const B& b, const Header& h, int k, int& out_x, i
 // legal_count.  Ascending action order is column-major (action = x*n+y,
 // twixtboard.cc:603-605), i.e. the order of the column words.
 template <class B>
-TW_HD void select_legal(const B& b, const Header& h, int k, int& out_x, int& out_y) {
+TW_HD void select_legal(const B& b, const Header& h, int k, int& out_x, int& out_y, uint32_t* out_pegs = nullptr) {
   if constexpr (B::kCountCache) {
-    select_legal_cached(b, h, k, out_x, out_y);
+    select_legal_cached(b, h, k, out_x, out_y, out_pegs);
   } else {
     int sx = 0, sk = 0;
     uint32_t sw = 0;

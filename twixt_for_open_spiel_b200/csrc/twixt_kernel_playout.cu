@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
   // The cell of the NEXT move is chosen one move ahead: between placing a peg and evaluating its links
   // (two independent dependency chains the scheduler can interleave), see the MOVE section.
   int sx = 0, sy = 0;
+  // the red / blue peg words of column sx as they stand (read while choosing the cell): begin_move takes the
+  // mover's from here instead of loading it again at the head of the loop-carried select -> place chain
+  uint32_t spegs[2] = {0u, 0u};
   int step = 0;
   // Border-flag floods owed: bits (2c, 2c+1) of `pend` = colour c still has to flood the START / END flag from
   // its newest peg `origin_of[c]`; `fcol` is the colour of the flood whose entries are on the stack.  A flood of
@@ -381,10 +384,11 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
       const int k = static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(n * (n - 2))));
       sx = 1 + k / n;
       sy = k - (sx - 1) * n;
+      spegs[0] = spegs[1] = 0u;  // an empty board
     } else {
       count_cache_build(b);
       if (playing)
-        select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy);
+        select_legal(b, h, static_cast<int>(playout_index(word_at(0u), static_cast<uint32_t>(legal_count(h, n)))), sx, sy, spegs);
     }
     sact = sx * n + sy;
     swap_next = playing && is_swap(h, static_cast<uint32_t>(sact));
@@ -449,7 +453,9 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
           }
         }
         if (swap_next) {  // possibly set by finish_take just now: a game taken over at ply 1
-          swap_first_move(b, h, sx, sy);
+          swap_first_move(b, h, sx, sy);  // takes the red peg back and turns (sx, sy): another column
+          spegs[0] = b.ld_pegs(P_RED, sx);
+          spegs[1] = b.ld_pegs(P_BLUE, sx);
           swap_next = false;
         }
       }
@@ -474,14 +480,14 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
     if (playing && !flood_blocks) {
       if (kTrace && step < a.trace_plies)
         a.out_actions[static_cast<int64_t>(step) * a.count + idx] = static_cast<uint16_t>(sact);
-      const Placement pl = begin_move</*kSwapDone=*/true>(b, h, sx, sy);
+      const Placement pl = begin_move</*kSwapDone=*/true, /*kPreloaded=*/true>(b, h, sx, sy, (h.ply & 1u) == kRed ? spegs[0] : spegs[1]);
       // choose the following move now (speculatively: unused if this move ends the game); it only reads the
       // peg planes and the count cache, which begin_move has just brought up to date
       Header hn = h;
       hn.ply = h.ply + 1u;
       const int ln = legal_count(hn, n);
       int nx, ny;
-      select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny);
+      select_legal(b, hn, static_cast<int>(playout_index(word_at(static_cast<uint32_t>(step) + 1u), static_cast<uint32_t>(ln))), nx, ny, spegs);
       uint32_t owed;
       const bool win = link_move</*kAlways=*/true>(b, pl, owed);
       finish_move(h, pl, win);
