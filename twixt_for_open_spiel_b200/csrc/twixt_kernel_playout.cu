@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
   // lane's strided column) of the header (parked in the idle flood-stack words) and the planes;
   // finish_take runs at the top of the next loop iteration, when the data has normally arrived.
   bool loading = false;
+  bool have = false;  // this lane holds an env (idx >= 0; a flag, because the 64-bit compare sat in every iteration's top)
   auto begin_take = [&](int64_t e) {
     idx = e;
+    have = true;
     grec = a.records + e * rw;
     for (int w = 0; w < kHeaderWords; ++w) __pipeline_memcpy_async(stk.base + w * 32, grec + w, 4);
     for (int w = 0; w < kSmemPlanes * n; ++w) __pipeline_memcpy_async(mine + b.smem_word(w) * 32, grec + kHeaderWords + w, 4);
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
     }
     t_swaps += h.swapped != swapped_before;
     idx = -1;
+    have = false;
   };
 
   // every thread only ever touches its own column of the staging buffer: no barrier needed anywhere.
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
     // ---- RARE (one branch region): an env whose copy was started an iteration ago is unpacked; a finished
     // env goes back to HBM and the lane starts copying the next one
     {
-      const bool done = idx >= 0 && !loading && !playing && pend == 0u && stk.empty();
+      const bool done = have && !loading && !playing && pend == 0u && stk.empty();
       if (loading || done || swap_next) {
         if (loading) {
           finish_take();
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(playout_threads(NT), playout_min_blocks(NT)) p
     }
     if ((it & 3u) == 0u) {  // warp-uniform
       // a lane only runs out of envs in the rare block above, so looking every fourth iteration is enough
-      if (!__any_sync(kFullMask, idx >= 0)) break;
+      if (!__any_sync(kFullMask, have)) break;
       // every lane that has moved into its second block of random words gets the next one
       if (static_cast<uint32_t>(step) + 1u >= 4u * (rq + 1u)) {  // step+1 = next word to be consumed
         rq += 1u;
