@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(kLegalWarps * 32) legal_mask_kernel(const uint
 // ---------------------------------------------------------------- apply ---
 // TwixTState::DoApplyAction (twixt.h:93-104): legality, Board::ApplyAction,
 // turn hand-over (implicit in ply parity / result).
-__global__ void apply_kernel(uint32_t* __restrict__ records, int64_t count, int n, int rw,
+// (the launch bound lets ptxas use 93 registers instead of the 64 its default heuristic stops at: the independent
+// loads of link_move stay in flight together, 0.2294 -> 0.2171 ms per 1 Mi envs)
+__global__ void __launch_bounds__(128, 1) apply_kernel(uint32_t* __restrict__ records, int64_t count, int n, int rw,
                              const int32_t* __restrict__ actions, int32_t* __restrict__ out_status,
                              DeviceStats* __restrict__ stats) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -307,7 +309,7 @@ __global__ void apply_kernel(uint32_t* __restrict__ records, int64_t count, int 
 // actions[i*stride + 0 .. len_i) in order from its CURRENT state with the legality test of DoApplyAction
 // (twixt.h:93-104); len_i = lengths[i] if given, else the row up to its first negative entry.  An env stops
 // at its first illegal action (state as reached so far); out_applied[i] = moves made.
-__global__ void replay_kernel(uint32_t* __restrict__ records, int64_t count, int n, int rw,
+__global__ void __launch_bounds__(128, 1) replay_kernel(uint32_t* __restrict__ records, int64_t count, int n, int rw,
                               const int32_t* __restrict__ actions, int64_t stride, const int32_t* __restrict__ lengths,
                               int32_t* __restrict__ out_applied, DeviceStats* __restrict__ stats) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
