@@ -10,6 +10,7 @@
 //   policy 2  policy 1 + the FLOOD region runs twice in iterations where at least T lanes owe visits
 //   policy 3  policy 1 + MOVE is skipped in iterations where fewer than T lanes are ready to move
 //   policy 4  policy 1 + the FLOOD region only runs every T-th iteration (visits are batched)
+//   policy 6  policy 1 + a second FLOOD pass, only for lanes whose next move is blocked by the flood, when >= T are
 //   policy 5  policy 1 + the FLOOD region only runs when at least T lanes owe a visit, or one has waited 3 iterations
 // Build: g++ -O2 -std=c++17 -I twixt_for_open_spiel_b200/csrc -o /tmp/warp_sim tools/warp_sim.cc
 #include <cstdint>
@@ -197,11 +198,26 @@ int main(int argc, char** argv) {
         for (int l = 0; l < 32; ++l) owing += L[l].have && (!L[l].stk.empty() || L[l].pendc[0] || L[l].pendc[1]);
         if (owing >= thresh) passes = 2;
       }
+      if (policy == 6) {
+        int blocked = 0;
+        for (int l = 0; l < 32; ++l) {
+          Lane& a = L[l];
+          if (!a.have || a.load_wait > 0) continue;
+          const int mover = static_cast<int>(a.h.ply & 1u);
+          const bool blk = a.pendc[mover] != 0u || (!a.stk.empty() && a.run_colour == mover);
+          blocked += blk;
+        }
+        if (blocked >= thresh) passes = 2;
+      }
       for (int p = 0; p < passes; ++p) {
         int nf = 0;
         for (int l = 0; l < 32; ++l) {
           Lane& a = L[l];
           if (!a.have || !(!a.stk.empty() || a.pendc[0] || a.pendc[1])) continue;
+          if (policy == 6 && p == 1) {  // second pass: only lanes whose next move waits for the flood
+            const int mover = static_cast<int>(a.h.ply & 1u);
+            if (!(a.pendc[mover] != 0u || (!a.stk.empty() && a.run_colour == mover))) continue;
+          }
           ++nf;
           ++visits;
           uint32_t e;
